@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the torchcde_b200 hot path against BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one fused fixed-step solve ``cdeint(CubicSpline(hermite coeffs), linear func, z0,
+t=[0, L-1], method='rk4', options={'step_size': 1})`` over one synthetic batch at BASELINE
+config 3: batch 65536 per GPU, length 256, 8 input channels, 32 hidden channels, fp32.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
+
+Timing rules: inputs resident in HBM for ``value`` (CUDA events, max over ranks, barrier +
+synchronize both sides); the coefficient tensor is 2.1 GB per GPU, far larger than the 126 MB
+L2, so no flush is needed between iterations.  ``e2e`` runs the same solve from pinned HOST
+buffers through ``torchcde_b200.hostio.cdeint_from_host`` with the copies inside the timed region.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+BATCH, LENGTH, CHANNELS, HIDDEN = 65536, 256, 8, 32
+METRIC = "sequences/s for cdeint RK4 (batch=65536,len=256,ch=8,hid=32)"
+# SURVEY.md 8(d) / BASELINE.md 4: algorithmic work per sequence of the fused RK4 solve
+BYTES_PER_SEQ = 255 * 3 * CHANNELS * 4 + HIDDEN * 4 + 2 * HIDDEN * 4           # 24,864 B
+FLOPS_PER_SEQ = 255 * (4 * (2 * HIDDEN * HIDDEN * CHANNELS + HIDDEN * CHANNELS + 2 * HIDDEN * CHANNELS + 4 * CHANNELS) + 320)
+HERMITE_BYTES_PER_SEQ = LENGTH * CHANNELS * 4 + (LENGTH - 1) * 4 * CHANNELS * 4   # 40,832 B
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "sm_max_mhz": p.get("sm_max_mhz", 1965.0),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------- synthetic data
+def synthetic(batch, device, seed):
+    """bounded random walk x = cumsum(randn)/sqrt(L); Linear(32, 256) default init; z0 ~ N(0,1)."""
+    import torchcde_b200 as cde
+    gen = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(batch, LENGTH, CHANNELS, generator=gen, device=device).cumsum(1) / math.sqrt(LENGTH)
+    z0 = torch.randn(batch, HIDDEN, generator=gen, device=device)
+    torch.manual_seed(1)
+    func = cde.LinearVectorField(HIDDEN, CHANNELS).to(device)
+    return x, z0, func
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.file:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val == "Active":
+                    reasons.add(name)
+        self.file.close()
+        os.unlink(self.file.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]                 # upper half = samples under load
+        return {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_loop(fn, steps, warmup, device, dist=None):
+    """W untimed + exactly K timed calls, CUDA events on the current stream, barrier + sync both sides."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        fn()
+    end.record()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    ms = start.elapsed_time(end)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_solve_sample(sample_paths, threads):
+    """The reference's CPU path for the same workload: its op sequence (oracle port) on host cores."""
+    from oracle import cde_oracle as O
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(sample_paths, LENGTH, CHANNELS, generator=gen).cumsum(1) / math.sqrt(LENGTH)
+    z0 = torch.randn(sample_paths, HIDDEN, generator=gen)
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(HIDDEN, HIDDEN * CHANNELS)
+    knots = O.knot_times(LENGTH, torch.float32)
+    t = torch.tensor([0.0, LENGTH - 1.0])
+    with torch.no_grad():
+        coeffs = O.hermite_backward_difference_coeffs(x)
+
+        def run():
+            return O.cdeint_linear(coeffs, knots, lin.weight, lin.bias, z0, t, "rk4", 1.0)
+    return run
+
+
+def cpu_baseline(sample_paths=4096, reps=2):
+    threads = os.cpu_count() or 1
+    run = cpu_solve_sample(sample_paths, threads)
+    with torch.no_grad():
+        run()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            run()
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_paths / dt, "unit": "sequences/s", "cores": threads, "kind": "port",
+            "sample": "{} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's order "
+                      "(oracle/cde_oracle.py + oracle/odeint_port.py), mean of {} runs after 1 warm-up; "
+                      "torchdiffeq itself is not installable here".format(sample_paths, reps)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 2048
+    run = cpu_solve_sample(sample, threads)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            run()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run()
+        total = time.perf_counter() - t0
+    value = sample * args.steps / total
+    base = {"value": value, "unit": "sequences/s", "cores": threads, "kind": "port",
+            "sample": "each step = {} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's op "
+                      "order (oracle port; torchdiffeq is not installable offline)".format(sample)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cdeint rk4 step_size=1 CubicSpline(hermite) linear func, sample of "
+                                   "batch=65536 len=256 ch=8 hid=32 on host CPU"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torchcde_b200 as cde
+    from torchcde_b200 import _lib, hostio
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    _lib.load()
+
+    x, z0, func = synthetic(BATCH, device, seed=1000 + rank)
+    if dist is not None:
+        from torchcde_b200.distributed import broadcast_field
+        broadcast_field(func, src=0)          # the one collective of the job: 8,448 floats over NCCL
+    options = {"step_size": 1.0}
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
+        X = cde.CubicSpline(coeffs)
+        t = torch.tensor([0.0, LENGTH - 1.0])      # == X.interval, kept on the host: no sync per call
+        holder = {}
+
+        def step():
+            holder["out"] = cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options=options)
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms = time_loop(step, args.steps, args.warmup, device, dist)
+        clocks = sampler.stop() if rank == 0 else None
+        assert bool(torch.isfinite(holder["out"]).all())
+
+        # ---- end to end from pinned host buffers (copies inside the timed region) ------------
+        coeffs_host = torch.empty(coeffs.shape, dtype=coeffs.dtype, pin_memory=True)
+        coeffs_host.copy_(coeffs)
+        z0_host = torch.empty(z0.shape, dtype=z0.dtype, pin_memory=True)
+        z0_host.copy_(z0)
+        out_host = torch.empty(BATCH, 2, HIDDEN, dtype=z0.dtype, pin_memory=True)
+        chunk = 4096
+        pipe = hostio.HostPipeline(device, chunk, tuple(coeffs.shape[1:]), HIDDEN, 2, coeffs.dtype)
+
+        def e2e_step():
+            hostio.cdeint_from_host(coeffs_host, func, z0_host, t, out_host=out_host, chunk_paths=chunk,
+                                    pipeline=pipe, device=device, method="rk4", options=options)
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_ms = time_loop(e2e_step, e2e_steps, 1, device, dist)
+        torch.cuda.synchronize(device)
+        e2e_ok = torch.equal(out_host.to(device), holder["out"])
+
+        # ---- secondary kernels (rank 0, N=1 only): the HBM-bound coefficient builders ---------
+        extra = {}
+        if rank == 0:
+            peaks = measured_peaks()
+            for name, fn in (("hermite_bdiff_coeffs", lambda: cde.hermite_cubic_coefficients_with_backward_differences(x)),
+                             ("natural_cubic_coeffs", lambda: cde.natural_cubic_coeffs(x))):
+                k_ms = time_loop(fn, 5, 3, device) / 5
+                gbs = BATCH * HERMITE_BYTES_PER_SEQ / (k_ms * 1e-3) / 1e9
+                extra[name] = {"ms": k_ms, "sequences_per_s": BATCH / (k_ms * 1e-3), "bound": "hbm",
+                               "achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+                               "algorithmic_bytes_per_seq": HERMITE_BYTES_PER_SEQ}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    ms_step = ms / args.steps
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    kernel_s = ms_step * 1e-3                       # one launch per step: the step IS the kernel
+    achieved_gbs = BATCH * BYTES_PER_SEQ / kernel_s / 1e9
+    achieved_tf = BATCH * FLOPS_PER_SEQ / kernel_s / 1e12
+    fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cdeint rk4 step_size=1 (255 steps, 1020 stage evals), CubicSpline(hermite bdiff "
+                               "coeffs), linear func Linear(32,256).view(32,8), batch=65536 per GPU, len=256, ch=8, "
+                               "hid=32, adjoint=False", "parallelism": "batch-sharded x{}".format(world),
+                   "global_batch": world * BATCH, "l2": "inputs (2.1 GB coeffs per GPU) exceed the 126 MB L2; no flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": coeffs_host.numel() * 4 + z0_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "torchcde_b200.hostio.cdeint_from_host (pinned host coeffs+z0 -> chunked H2D / fused solve / D2H "
+                       "on 2 streams)", "matches_device_result": bool(e2e_ok)},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                     "kernel": "cdeint_simt_kernel<float,8,8>", "algorithmic_bytes_per_launch": BATCH * BYTES_PER_SEQ,
+                     "note": "this kernel is FP32-FMA bound (708 flop/B), not HBM bound; see fp32 below and DESIGN.md",
+                     "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak_tf,
+                              "frac": achieved_tf / fp32_peak_tf,
+                              "peak_source": "148 SMs x 128 FMA lanes x 2 x clocks.max.sm"}},
+        "kernels": extra,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

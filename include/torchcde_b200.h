@@ -1,0 +1,156 @@
+/*
+ * torchcde_b200 -- C ABI of the B200-native Neural-CDE hot path.
+ *
+ * The reference (patrick-kidger/torchcde) is pure Python and has no FFI of its own; the
+ * drop-in boundary is its Python API.  This header is the boundary one level
+ * below: the entry points the Python host layer (torchcde_b200/*.py) binds with ctypes, and
+ * that a reference maintainer would bind the same way (INTEGRATION.md shows the stubs).
+ * Each entry point names the reference function whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.  All data pointers are DEVICE
+ *     pointers owned by the caller, contiguous, row-major.  Nothing is allocated inside.
+ *   - `dtype`: TCDE_F32 or TCDE_F64 -- the dtype of every floating-point buffer of the call.
+ *   - `stream`: a cudaStream_t passed as void* (NULL = legacy default stream).  Every call
+ *     only enqueues work on that stream and returns; it never synchronises.
+ *   - return value: TCDE_OK (0) or a negative tcde_status; tcde_last_error() gives the text
+ *     of the last failure on the calling thread.  Nothing throws across the boundary.
+ *   - a "series" is one scalar time series (one batch element, one channel); a "path" is one
+ *     batch element with all its channels: x[n_paths][length][channels].
+ *   - spline coefficient rows follow the reference layout (interpolation_cubic.py:297-305):
+ *     coeffs[n_paths][length-1][4*channels] with row = [a | b | 2c | 3d].
+ */
+#ifndef TORCHCDE_B200_H
+#define TORCHCDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCDE_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TCDE_API __attribute__((visibility("default")))
+#else
+#define TCDE_API
+#endif
+
+enum tcde_dtype { TCDE_F32 = 0, TCDE_F64 = 1 };
+
+enum tcde_status {
+    TCDE_OK = 0,
+    TCDE_ERR_ARGUMENT = -1,     /* null pointer, non-positive size, unknown enum */
+    TCDE_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels are built for (message says which) */
+    TCDE_ERR_CUDA = -3          /* a CUDA runtime call failed (message carries cudaGetErrorString) */
+};
+
+enum tcde_control { TCDE_CONTROL_CUBIC = 0, TCDE_CONTROL_LINEAR = 1 };
+enum tcde_method { TCDE_EULER = 0, TCDE_MIDPOINT = 1, TCDE_RK4_38 = 2 };
+
+/* flag bits written by the builders into *flags (a device int32, may be NULL) */
+#define TCDE_FLAG_NAN_SEEN 1        /* at least one NaN in x */
+#define TCDE_FLAG_NAN_TIME 2        /* rectilinear: NaN in the time channel */
+#define TCDE_FLAG_NAN_FIRST_ROW 4   /* rectilinear: NaN in the first row of some channel */
+
+TCDE_API int tcde_abi_version(void);
+TCDE_API const char* tcde_last_error(void);
+/* number of SMs / compute capability of the current device; 0 on success */
+TCDE_API int tcde_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- hot path (i): coefficient construction ------------------------------------------- */
+
+/* hermite_cubic_coefficients_with_backward_differences on NaN-free knots
+ * (interpolation_hermite_cubic_bdiff.py:5-44, after the linear fill at :33).
+ * x[n_paths][length][channels] -> coeffs[n_paths][length-1][4*channels].
+ * t: length knots, or NULL for the default 0,1,...,length-1 (misc.py:79-80).
+ * Bit-identical to the reference's fp32/fp64 result.  Sets TCDE_FLAG_NAN_SEEN if x holds a
+ * NaN (the caller then runs tcde_linear_fill and calls again, as the reference does). */
+TCDE_API int tcde_hermite_bdiff_coeffs(const void* x, const void* t, void* coeffs, int64_t n_paths, int64_t length,
+                              int64_t channels, int dtype, int32_t* flags, void* stream);
+
+/* linear_interpolation_coeffs with missing values, per series
+ * (interpolation_linear.py:13-84): all-NaN -> zeros; missing ends take the first / last
+ * observation; interior gaps are interpolated in time.  x -> out, same shape.  Bit-identical. */
+TCDE_API int tcde_linear_fill(const void* x, const void* t, void* out, int64_t n_paths, int64_t length,
+                     int64_t channels, int dtype, void* stream);
+
+/* torch.isnan(x).any() (the branch selector at interpolation_linear.py:169 and
+ * interpolation_cubic.py:176) over n elements: sets TCDE_FLAG_NAN_SEEN in *flags. */
+TCDE_API int tcde_nan_flag(const void* x, int64_t n, int dtype, int32_t* flags, void* stream);
+
+/* misc.forward_fill along the length dim (misc.py:103-126); leading NaNs stay NaN. */
+TCDE_API int tcde_forward_fill(const void* x, void* out, int64_t n_paths, int64_t length, int64_t channels,
+                      int dtype, int32_t* flags, void* stream);
+
+/* _prepare_rectilinear_interpolation (interpolation_linear.py:87-128):
+ * x[n_paths][length][channels] -> out[n_paths][2*length-1][channels].
+ * Sets TCDE_FLAG_NAN_TIME / TCDE_FLAG_NAN_FIRST_ROW for the caller's assertion / warning. */
+TCDE_API int tcde_rectilinear_prepare(const void* x, void* out, int64_t n_paths, int64_t length, int64_t channels,
+                             int64_t time_index, int dtype, int32_t* flags, void* stream);
+
+/* natural cubic spline on NaN-free knots (interpolation_cubic.py:7-53 + the Thomas solve of
+ * misc.py:13-67).  workspace: device scratch of 4*length elements of `dtype` (the eliminated
+ * diagonal, shared by every series, is formed once there).  fp tolerance: a few ulp (the
+ * back-substitution multiplies by a reciprocal instead of dividing).  Sets
+ * TCDE_FLAG_NAN_SEEN like the Hermite builder. */
+TCDE_API int tcde_natural_cubic_coeffs(const void* x, const void* t, void* coeffs, void* workspace, int64_t n_paths,
+                              int64_t length, int64_t channels, int dtype, int32_t* flags, void* stream);
+
+/* natural cubic spline with missing values, per series (interpolation_cubic.py:56-167).
+ * version 0 = natural_cubic_spline_coeffs (ends copied), 1 = natural_cubic_coeffs (ends
+ * filled).  scratch: device memory of tcde_natural_cubic_missing_scratch_bytes() bytes. */
+TCDE_API int64_t tcde_natural_cubic_missing_scratch_bytes(int64_t n_paths, int64_t length, int64_t channels, int dtype);
+TCDE_API int tcde_natural_cubic_coeffs_missing(const void* x, const void* t, void* coeffs, void* scratch, int64_t n_paths,
+                                      int64_t length, int64_t channels, int version, int dtype, void* stream);
+
+/* ---- hot path (ii): spline evaluation and the fused fixed-step solve ------------------- */
+
+/* CubicSpline.evaluate / .derivative (interpolation_cubic.py:324-336) or
+ * LinearInterpolation.evaluate / .derivative (interpolation_linear.py:212-225) at n_times
+ * query points whose interval index / fraction the host already located
+ * (index[n_times] int32, frac[n_times]).  out[n_paths][n_times][channels].
+ * control = coeffs (cubic) or knot values (linear, with knot_t[length]). */
+TCDE_API int tcde_spline_eval(const void* control, const void* knot_t, const int32_t* index, const void* frac,
+                     void* out, int64_t n_paths, int64_t n_rows, int64_t channels, int64_t n_times,
+                     int control_kind, int derivative, int dtype, void* stream);
+
+/* One evaluation of the CDE vector field for the README-form linear func
+ * (solver.py:117-135 with func = Linear(H, H*C).view(H, C)):
+ *   out[p][h] = sum_c (bias[h*C+c] + sum_k weight[h*C+c][k] z[p][k]) * dXdt[p][c]
+ * with dXdt taken from the control at (index, frac).  Used by the adaptive driver. */
+TCDE_API int tcde_vector_field_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                             const void* bias, const void* z, void* out, int64_t n_paths, int64_t channels,
+                             int64_t hidden, int32_t index, double frac, int dtype, void* stream);
+
+/* The fused fixed-step solve: everything torchdiffeq's fixed-grid odeint does for
+ * cdeint(X, func, z0, t, method in {euler, midpoint, rk4}, options={step_size})
+ * (solver.py:224-236; stepping restated in oracle/odeint_port.py) in ONE kernel launch:
+ * spline derivative, linear vector field, f.dX/dt contraction, Runge-Kutta combination and
+ * output interpolation, with the state in registers across all steps.
+ *
+ *   control      cubic: coeffs[n_paths][n_rows][4C];  linear: slopes[n_paths][n_rows][C]
+ *   weight,bias  Linear(H, H*C): weight[H*C][H], bias[H*C]
+ *   z0           [n_paths][H]
+ *   out          [n_paths][n_out][H]      (time on dim -2, like solver.py:234-236)
+ *   schedule (host-built with the reference's own torch ops, torchcde_b200/schedule.py):
+ *     step_dt[n_steps]                     step width, already in the state dtype
+ *     stage_index[n_steps][n_stages] int32 interval index of every stage time (bit-exact
+ *                                          with CubicSpline._interpret_t), stage_frac same shape
+ *     out_step[n_out] int32                step after which output j is produced (-1: j is z0)
+ *     out_mode[n_out] int32                0 = copy step start, 1 = copy step end, 2 = interpolate
+ *     out_slope[n_out]                     interpolation weight for mode 2
+ *   sign         +1, or -1 for a decreasing t (field negated, torchdiffeq's time reversal)
+ */
+TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                             const void* bias, const void* z0, void* out, int64_t n_paths, int64_t channels,
+                             int64_t hidden, int method, int64_t n_steps, const void* step_dt,
+                             const int32_t* stage_index, const void* stage_frac, int64_t n_out,
+                             const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
+                             double sign, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORCHCDE_B200_H */

@@ -1,0 +1,130 @@
+"""Host-side logic that needs no GPU: validation, the fixed-step schedule, func recognition."""
+import pytest
+import torch
+
+import torchcde_b200 as cde
+from oracle import cde_oracle as O
+from oracle import odeint_port
+from torchcde_b200 import schedule, solver
+
+
+def test_validation_errors_match_reference_wording():
+    f = cde.hermite_cubic_coefficients_with_backward_differences
+    with pytest.raises(ValueError, match="floating point"):
+        f(torch.zeros(3, 2, dtype=torch.int64))
+    with pytest.raises(ValueError, match="at least two dimensions"):
+        f(torch.zeros(3))
+    with pytest.raises(ValueError, match="monotonically increasing"):
+        f(torch.zeros(3, 2), torch.tensor([0.0, 2.0, 1.0]))
+    with pytest.raises(ValueError, match="one dimensional"):
+        cde.natural_cubic_coeffs(torch.zeros(3, 2), torch.zeros(3, 1))
+    with pytest.raises(ValueError, match="time dimension of X must equal"):
+        cde.linear_interpolation_coeffs(torch.zeros(3, 2), torch.tensor([0.0, 1.0]))
+    with pytest.raises(ValueError, match="at least 2"):
+        cde.natural_cubic_spline_coeffs(torch.zeros(1, 2))
+    with pytest.raises(ValueError, match="invalid coeffs"):
+        cde.CubicSpline(torch.zeros(2, 3, 7))
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cde.hermite_cubic_coefficients_with_backward_differences(torch.zeros(2, 5, 3))
+    X = cde.CubicSpline(torch.zeros(2, 4, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        X.derivative(torch.tensor(0.5))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cde.cdeint(X, cde.LinearVectorField(3, 2), torch.zeros(2, 3), X.interval, adjoint=False, method="rk4",
+                   options={"step_size": 1.0})
+
+
+def test_cdeint_argument_errors():
+    X = cde.CubicSpline(torch.zeros(2, 4, 8))
+    f = cde.LinearVectorField(3, 2)
+    z0 = torch.zeros(2, 3)
+    with pytest.raises(ValueError, match="Unrecognised backend"):
+        cde.cdeint(X, f, z0, X.interval, backend="nope", method="rk4")
+    with pytest.raises(ValueError, match="'derivative' method"):
+        cde.cdeint(object(), f, z0, X.interval, method="rk4")
+    with pytest.raises(NotImplementedError, match="dopri5"):
+        cde.cdeint(X, f, z0, X.interval)
+    with pytest.raises(ValueError, match="batch dimensions"):
+        cde.cdeint(X, f, torch.zeros(5, 3), X.interval, adjoint=False, method="rk4")
+    with pytest.raises(NotImplementedError, match="torchsde"):
+        cde.cdeint(X, f, z0, X.interval, backend="torchsde")
+
+
+def test_spline_buffers_are_views_with_reference_names():
+    coeffs = torch.randn(2, 5, 12)
+    X = cde.CubicSpline(coeffs)
+    assert [n for n, _ in X.named_buffers()] == ["_t", "_a", "_b", "_two_c", "_three_d"]
+    assert X._b.data_ptr() == coeffs[..., 3:6].data_ptr()          # interpolation_cubic.py:297-305
+    assert X.interval.tolist() == [0.0, 5.0] and X.grid_points.numel() == 6
+    lin = cde.LinearInterpolation(torch.randn(2, 5, 3))
+    assert [n for n, _ in lin.named_buffers()] == ["_t", "_coeffs"]
+
+
+@pytest.mark.parametrize("dtype_t", [torch.float32, torch.float64])
+@pytest.mark.parametrize("method,step", [("rk4", 1.0), ("rk4", 0.4), ("midpoint", 0.5), ("euler", 0.25), ("rk4", None)])
+def test_schedule_reproduces_the_stage_by_stage_arithmetic(dtype_t, method, step):
+    """Drive the oracle's solver with a recording field and compare every stage's interval and
+    fraction, computed one stage at a time the reference's way, with the batched table."""
+    knots = (torch.rand(12, dtype=torch.float64) + 0.2).cumsum(0).float()
+    lo, hi = float(knots[0]), float(knots[-1])
+    t = torch.tensor([lo, lo + 0.37 * (hi - lo), lo + 0.5 * (hi - lo), hi], dtype=dtype_t)
+    seen = []
+
+    def field(s, y):
+        frac, idx = O.locate(knots, s, 11)
+        seen.append((int(idx), float(frac)))
+        return y * 0
+
+    options = {} if step is None else {"step_size": step}
+    odeint_port.odeint(field, torch.zeros(1), t, method=method, options=options)
+    sched = schedule.build_schedule(t, knots, 11, method, step, torch.float32)
+    flat_idx = sched.stage_index.reshape(-1).tolist()
+    flat_frac = sched.stage_frac.reshape(-1).tolist()
+    assert len(seen) == len(flat_idx)
+    assert [s[0] for s in seen] == flat_idx                 # interval indices: bit exact
+    assert [s[1] for s in seen] == flat_frac
+    assert sched.out_step[0] == -1 and sched.n_out == 4
+
+
+def test_schedule_knot_semantics_and_reversal():
+    knots = torch.linspace(0, 255, 256)
+    s = schedule.build_schedule(torch.tensor([0.0, 255.0]), knots, 255, "rk4", 1.0, torch.float32)
+    assert s.n_steps == 255 and s.stage_index[0].tolist() == [0, 0, 0, 0]
+    # step n > 0: k1 sits exactly on knot n and reads interval n-1 with fraction 1
+    assert s.stage_index[7].tolist() == [6, 7, 7, 7] and float(s.stage_frac[7, 0]) == 1.0
+    r = schedule.build_schedule(torch.tensor([255.0, 0.0]), knots, 255, "rk4", 1.0, torch.float32)
+    assert r.sign == -1.0 and r.stage_index[0].tolist() == [254, 254, 254, 253]
+    with pytest.raises(ValueError):
+        schedule.build_schedule(torch.tensor([0.0, 1.0, 0.5]), knots, 255, "rk4", 1.0, torch.float32)
+
+
+def test_linear_field_recognition():
+    z0 = torch.randn(4, 3)
+    t0 = torch.tensor(0.0)
+    good = cde.LinearVectorField(3, 2)
+    assert solver.linear_field_of(good, z0, 2, t0)[0] is good.linear.weight
+    assert solver.linear_field_of(good, z0, 5, t0) is None            # wrong channel count
+
+    class Readme(torch.nn.Module):                                     # README.md:42-49
+        def __init__(self):
+            super().__init__()
+            self.linear = torch.nn.Linear(3, 6)
+
+        def forward(self, t, z):
+            return self.linear(z).view(4, 3, 2)
+
+    class WithTanh(Readme):
+        def forward(self, t, z):
+            return self.linear(z).view(4, 3, 2).tanh()
+
+    class Transposed(Readme):
+        def forward(self, t, z):
+            return self.linear(z).view(4, 2, 3).transpose(-1, -2)
+
+    assert solver.linear_field_of(Readme(), z0, 2, t0) is not None
+    assert solver.linear_field_of(WithTanh(), z0, 2, t0) is None
+    assert solver.linear_field_of(Transposed(), z0, 2, t0) is None
+    assert solver.linear_field_of(lambda t, z: z, z0, 2, t0) is None

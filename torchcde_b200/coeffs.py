@@ -1,0 +1,222 @@
+"""Coefficient construction -- the host side of hot path (i).
+
+Same names, arguments, shapes, exception types and messages as the reference builders
+(interpolation_linear.py:131-171, interpolation_hermite_cubic_bdiff.py:23-44,
+interpolation_cubic.py:173-265, misc.py:70-126); the arithmetic runs in the CUDA kernels of
+``csrc/builders.cu`` through the C ABI.  CUDA tensors only; float32 / float64.
+"""
+import math
+import warnings
+
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------- validation
+def validate_input_path(x, t):
+    """misc.py:70-100.  One vectorised monotonicity test instead of a Python loop over ``t``."""
+    if not x.is_floating_point():
+        raise ValueError("X must both be floating point.")
+
+    if x.ndimension() < 2:
+        raise ValueError("X must have at least two dimensions, corresponding to time and channels. It instead has "
+                         "shape {}.".format(tuple(x.shape)))
+
+    if t is None:
+        t = torch.linspace(0, x.size(-2) - 1, x.size(-2), dtype=x.dtype, device=x.device)
+
+    if not t.is_floating_point():
+        raise ValueError("t must both be floating point.")
+    if len(t.shape) != 1:
+        raise ValueError("t must be one dimensional. It instead has shape {}.".format(tuple(t.shape)))
+    if t.numel() > 0 and (bool((t[1:] <= t[:-1]).any()) or not bool(t[0] > -math.inf)):
+        raise ValueError("t must be monotonically increasing.")
+
+    if x.size(-2) != t.size(0):
+        raise ValueError("The time dimension of X must equal the length of t. X has shape {} and t has shape {}, "
+                         "corresponding to time dimensions of {} and {} respectively."
+                         .format(tuple(x.shape), tuple(t.shape), x.size(-2), t.size(0)))
+
+    if t.size(0) < 2:
+        raise ValueError("Must have a time dimension of size at least 2. It instead has shape {}, corresponding to a "
+                         "time dimension of size {}.".format(tuple(t.shape), t.size(0)))
+
+    return t
+
+
+def _no_autograd(name, *tensors):
+    if torch.is_grad_enabled() and any(x is not None and x.requires_grad for x in tensors):
+        raise NotImplementedError(
+            "torchcde_b200.{}: differentiating through the coefficient builders is not implemented; build the "
+            "coefficients under torch.no_grad() (they are preprocessing, interpolation_cubic.py:216-226).".format(name))
+
+
+def _paths(x):
+    """(..., L, C) -> contiguous (P, L, C) view / copy plus the batch shape."""
+    batch = x.shape[:-2]
+    flat = x.reshape(-1, x.size(-2), x.size(-1))
+    if not flat.is_contiguous():
+        flat = flat.contiguous()
+    return flat, batch
+
+
+def _knots_arg(t_given, x):
+    """Device knots in x's dtype for the kernels, or None for the default 0..L-1."""
+    if t_given is None:
+        return None
+    return t_given.to(device=x.device, dtype=x.dtype).contiguous()
+
+
+def _flags(x):
+    return torch.zeros(1, dtype=torch.int32, device=x.device)
+
+
+def _has_nan(flat):
+    flags = _flags(flat)
+    _lib.call("tcde_nan_flag", _lib.ptr(flat), flat.numel(), _lib.dtype_code(flat.dtype), _lib.ptr(flags),
+              _lib.stream_of(flat))
+    return bool(flags.item() & _lib.FLAG_NAN_SEEN)
+
+
+def _fill(flat, knots):
+    out = torch.empty_like(flat)
+    p, length, channels = flat.shape
+    _lib.call("tcde_linear_fill", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length, channels,
+              _lib.dtype_code(flat.dtype), _lib.stream_of(flat))
+    return out
+
+
+# --------------------------------------------------------------------------- linear / fills
+def forward_fill(x, fill_index=-2):
+    """misc.forward_fill (misc.py:103-126)."""
+    assert isinstance(x, torch.Tensor)
+    assert x.dim() >= 2
+    _lib.require_cuda(x)
+    _lib.dtype_code(x.dtype)
+    _no_autograd("forward_fill", x)
+    moved = x.movedim(fill_index, -2) if fill_index not in (-2, x.dim() - 2) else x
+    with torch.cuda.device(x.device):
+        flat, batch = _paths(moved)
+        out = torch.empty_like(flat)
+        flags = _flags(flat)
+        p, length, channels = flat.shape
+        _lib.call("tcde_forward_fill", _lib.ptr(flat), _lib.ptr(out), p, length, channels,
+                  _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
+    out = out.view(*batch, length, channels)
+    return out.movedim(-2, fill_index) if moved is not x else out
+
+
+def _prepare_rectilinear_interpolation(data, time_index):
+    """interpolation_linear.py:87-128 (same assertions).  Returns (prepared, starts_with_nan)."""
+    n_channels = data.size(-1)
+    assert isinstance(time_index, int), "Index of the time channel must be an integer in [0, {}]".format(n_channels - 1)
+    assert 0 <= time_index < n_channels, "Time index must be in [0, {}], was given {}." \
+                                         "".format(n_channels - 1, time_index)
+    flat, batch = _paths(data)
+    p, length, channels = flat.shape
+    out = torch.empty(p, 2 * length - 1, channels, dtype=flat.dtype, device=flat.device)
+    flags = _flags(flat)
+    _lib.call("tcde_rectilinear_prepare", _lib.ptr(flat), _lib.ptr(out), p, length, channels, time_index,
+              _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
+    seen = int(flags.item())
+    assert not (seen & _lib.FLAG_NAN_TIME), \
+        "There exist nan values in the time column which is not allowed. If the " \
+        "times are padded with nans after final time, a simple solution is to " \
+        "forward fill the final time."
+    return out.view(*batch, 2 * length - 1, channels), bool(seen & _lib.FLAG_NAN_FIRST_ROW)
+
+
+def linear_interpolation_coeffs(x, t=None, rectilinear=None):
+    """interpolation_linear.py:131-171.  Without NaNs (and without ``rectilinear``) the input
+    tensor itself is returned, like the reference (:169-171)."""
+    if not x.is_floating_point():
+        raise ValueError("X must both be floating point.")
+    if rectilinear is None:
+        validate_input_path(x, t)
+    _lib.require_cuda(x, t)
+    _lib.dtype_code(x.dtype)
+    _no_autograd("linear_interpolation_coeffs", x, t)
+    with torch.cuda.device(x.device):
+        if rectilinear is not None:
+            if x.ndimension() < 2:
+                validate_input_path(x, t)
+            x, starts_with_nan = _prepare_rectilinear_interpolation(x, rectilinear)
+            if starts_with_nan:
+                warnings.warn("The data `x` begins with missing values in some channels. The path will be constructed "
+                              "by backward-filling the first observed value, which is not causal. Raising a warning as "
+                              "the `rectilinear` argument has also been passed, which is nearly always only used when "
+                              "causality is desired. If you need causality then fill in the missing value at the start "
+                              "of each channel with whatever you'd like it to be. (The mean over that channel is a "
+                              "common choice.)")
+            t_full = validate_input_path(x, t)
+            has_nan = starts_with_nan
+        else:
+            t_full = validate_input_path(x, t)
+            _lib.dtype_code(x.dtype)
+            flat, batch = _paths(x)
+            has_nan = _has_nan(flat)
+        if not has_nan:
+            return x
+        flat, batch = _paths(x)
+        knots = None if t is None else _knots_arg(t_full, x)
+        out = _fill(flat, knots)
+        return out.view(*batch, x.size(-2), x.size(-1))
+
+
+# --------------------------------------------------------------------------- Hermite
+def hermite_cubic_coefficients_with_backward_differences(x, t=None):
+    """interpolation_hermite_cubic_bdiff.py:23-44: (..., L, C) -> (..., L-1, 4C)."""
+    t_full = validate_input_path(x, t)
+    _lib.require_cuda(x, t)
+    _no_autograd("hermite_cubic_coefficients_with_backward_differences", x, t)
+    with torch.cuda.device(x.device):
+        flat, batch = _paths(x)
+        p, length, channels = flat.shape
+        code = _lib.dtype_code(flat.dtype)
+        knots = None if t is None else _knots_arg(t_full, x)
+        out = torch.empty(p, length - 1, 4 * channels, dtype=flat.dtype, device=flat.device)
+        flags = _flags(flat)
+        stream = _lib.stream_of(flat)
+        _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length, channels,
+                  code, _lib.ptr(flags), stream)
+        if flags.item() & _lib.FLAG_NAN_SEEN:
+            # the reference fills first (bdiff.py:33); the kernel above told us it is needed
+            filled = _fill(flat, knots)
+            _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(filled), _lib.ptr(knots), _lib.ptr(out), p, length,
+                      channels, code, None, stream)
+    return out.view(*batch, length - 1, 4 * channels)
+
+
+# --------------------------------------------------------------------------- natural cubic
+def _natural(x, t, version, name):
+    t_full = validate_input_path(x, t)
+    _lib.require_cuda(x, t)
+    _no_autograd(name, x, t)
+    with torch.cuda.device(x.device):
+        flat, batch = _paths(x)
+        p, length, channels = flat.shape
+        code = _lib.dtype_code(flat.dtype)
+        knots = None if t is None else _knots_arg(t_full, x)
+        out = torch.empty(p, length - 1, 4 * channels, dtype=flat.dtype, device=flat.device)
+        flags = _flags(flat)
+        stream = _lib.stream_of(flat)
+        workspace = torch.empty(4 * length, dtype=flat.dtype, device=flat.device)
+        _lib.call("tcde_natural_cubic_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), _lib.ptr(workspace),
+                  p, length, channels, code, _lib.ptr(flags), stream)
+        if flags.item() & _lib.FLAG_NAN_SEEN:
+            nbytes = _lib.load().tcde_natural_cubic_missing_scratch_bytes(p, length, channels, code)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+            _lib.call("tcde_natural_cubic_coeffs_missing", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out),
+                      _lib.ptr(scratch), p, length, channels, version, code, stream)
+    return out.view(*batch, length - 1, 4 * channels)
+
+
+def natural_cubic_spline_coeffs(x, t=None):
+    """Deprecated variant (ends copied, interpolation_cubic.py:193-230)."""
+    return _natural(x, t, 0, "natural_cubic_spline_coeffs")
+
+
+def natural_cubic_coeffs(x, t=None):
+    """interpolation_cubic.py:233-265: (..., L, C) -> (..., L-1, 4C)."""
+    return _natural(x, t, 1, "natural_cubic_coeffs")

@@ -1,0 +1,737 @@
+// Hot path (i): batched spline-coefficient construction (sm_100a).
+//
+// All kernels here are HBM-bound streaming kernels (~1 flop per byte).  The
+// design rules that matter are the memory ones: coalesced loads, results staged in shared
+// memory and written back as one contiguous 1-D bulk (TMA) store per tile, persistent CTAs
+// sized from the SM count.  Arithmetic uses tcde::exact<> (one rounding per operation, no
+// FMA contraction) wherever the header promises bit-identical results.
+#include "common.cuh"
+
+namespace tcde {
+
+static constexpr int kThreads = 256;
+
+// =========================================================================================
+// Hermite cubic with backward differences  (interpolation_hermite_cubic_bdiff.py:5-44)
+// =========================================================================================
+// Work item = (path, tile of TR consecutive intervals).  The CTA stages the TR+2 knot rows it
+// needs in shared memory, every thread produces the four coefficients of its (interval,
+// channel) elements into a shared output tile laid out exactly like global memory
+// ([row][a|b|2c|3d][channel]), and one thread issues a single bulk store of the tile (the
+// tile is a contiguous byte range of the output).  Two output tiles alternate so that the
+// store of tile n overlaps the computation of tile n+1.
+template <typename T, bool UNIT>
+__global__ void __launch_bounds__(kThreads)
+hermite_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_paths, int L, int C,
+               int TR, int tiles_per_path, int use_bulk, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using E = exact<T>;
+    const int row_elems = 4 * C;
+    T* ot0 = reinterpret_cast<T*>(smem_raw);
+    T* ot1 = ot0 + (size_t)TR * row_elems;
+    T* xs = ot1 + (size_t)TR * row_elems;
+    T* ts = xs + (size_t)(TR + 2) * C;
+
+    const int tid = threadIdx.x;
+    const int di = kThreads / C, dc = kThreads - di * C;   // (row, channel) advance per thread-stride
+    const int i_first = tid / C, c_first = tid - i_first * C;
+    const int64_t n_items = n_paths * tiles_per_path;
+    bool saw_nan = false;
+    int buf = 0;
+
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+        const int64_t p = item / tiles_per_path;
+        const int tile = (int)(item - p * tiles_per_path);
+        const int r0 = tile * TR;
+        const int nr = min(TR, L - 1 - r0);
+        if (use_bulk && tid == 0) bulk_wait_read<1>();   // the store that last read ot[buf] has drained
+
+        // knot rows r0-1 .. r0+nr ; row -1 does not exist for the first tile
+        const T* xp = x + (p * L + r0 - 1) * C;
+        const int ne = (nr + 2) * C;
+        for (int e = (r0 == 0 ? C : 0) + tid; e < ne; e += kThreads) xs[e] = xp[e];
+        if (!UNIT) {
+            for (int e = (r0 == 0 ? 1 : 0) + tid; e < nr + 2; e += kThreads) ts[e] = t[r0 - 1 + e];
+        }
+        __syncthreads();
+
+        T* ot = buf ? ot1 : ot0;
+        int i = i_first, c = c_first;
+        for (int e = tid; e < nr * C; e += kThreads) {
+            const T xl = xs[(i + 1) * C + c];
+            const T xh = xs[(i + 2) * C + c];
+            saw_nan |= is_nan(xl) | is_nan(xh);
+            const bool first = (r0 + i == 0);
+            T b, two_c, three_d;
+            if (UNIT) {
+                // dt == 1 exactly: every division by dt and the 1/dt^2 factor are exact identities
+                const T dn = E::sub(xh, xl);
+                const T dp = first ? dn : E::sub(xl, xs[i * C + c]);
+                const T bend = E::sub(dn, dp);
+                const T inner = E::add(E::sub(E::mul(T(3), bend), dn), dp);
+                two_c = E::mul(T(2), inner);
+                three_d = E::sub(bend, two_c);
+                b = dp;
+            } else {
+                const T dt = E::sub(ts[i + 2], ts[i + 1]);
+                const T dn = E::div(E::sub(xh, xl), dt);                       // bdiff.py:39
+                const T dp = first ? dn : E::div(E::sub(xl, xs[i * C + c]), E::sub(ts[i + 1], ts[i]));
+                const T inner = E::add(E::sub(E::mul(T(3), E::sub(dn, dp)), dn), dp);
+                two_c = E::div(E::mul(T(2), inner), dt);                        // bdiff.py:17
+                const T inv_sq = E::div(T(1), E::mul(dt, dt));
+                three_d = E::sub(E::mul(inv_sq, E::sub(dn, dp)), E::div(two_c, dt));   // bdiff.py:18
+                b = dp;
+            }
+            // four stores per thread; rotating which coefficient goes first by row spreads a
+            // warp's stores over all 32 banks (rows are 4C words apart)
+            T* row = ot + (size_t)i * row_elems + c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int w = (k + i) & 3;
+                const T v = (w == 0) ? xl : (w == 1) ? b : (w == 2) ? two_c : three_d;
+                row[w * C] = v;
+            }
+            i += di;
+            c += dc;
+            if (c >= C) { c -= C; ++i; }
+        }
+        T* gp = out + (p * (int64_t)(L - 1) + r0) * row_elems;
+        if (use_bulk) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store(gp, ot, (uint32_t)((size_t)nr * row_elems * sizeof(T)));
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int e = tid; e < nr * row_elems; e += kThreads) gp[e] = ot[e];
+        }
+    }
+    if (use_bulk && tid == 0) bulk_wait_read<0>();
+    if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
+}
+
+// =========================================================================================
+// Per-series scans: linear gap fill, forward fill, rectilinear preparation
+// =========================================================================================
+// One thread per scalar series, walking the length dimension.  A warp covers 32/C paths x C
+// channels, so every load/store instruction touches whole 32-byte sectors (C >= 8 floats) and
+// the four sectors of a 128-byte line are consumed by four consecutive iterations (L1 hits).
+// Loads do not depend on the scan state, so they are issued eight steps ahead.
+template <typename T, bool UNIT>
+__global__ void __launch_bounds__(kThreads)
+linear_fill_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_series, int L,
+                   int C) {
+    using E = exact<T>;
+    const int64_t g = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    if (g >= n_series) return;
+    const int64_t p = g / C;
+    const int c = (int)(g - p * C);
+    const T* xs = x + p * L * C + c;
+    T* os = out + p * L * C + c;
+
+    auto time_of = [&](int i) -> T { return UNIT ? T(i) : t[i]; };
+    // interpolation_linear.py:60-69: x[j] = lo + ((t_j - t_lo) / (t_hi - t_lo)) * (hi - lo)
+    auto bridge = [&](int lo, T vlo, int hi, T vhi) {
+        const T tl = time_of(lo);
+        const T span = E::sub(time_of(hi), tl);
+        const T rise = E::sub(vhi, vlo);
+        for (int j = lo + 1; j < hi; ++j) {
+            const T ratio = E::div(E::sub(time_of(j), tl), span);
+            os[(int64_t)j * C] = E::add(vlo, E::mul(ratio, rise));
+        }
+    };
+
+    int prev = -1;
+    T vprev = T(0);
+    for (int i0 = 0; i0 < L; i0 += 8) {
+        T ahead[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ahead[k] = (i0 + k < L) ? xs[(int64_t)(i0 + k) * C] : T(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k;
+            if (i < L && !is_nan(ahead[k])) {
+                const T v = ahead[k];
+                if (prev < 0) {
+                    if (i > 0) {            // :31-32 the first entry takes the first observation
+                        os[0] = v;
+                        bridge(0, v, i, v);
+                    }
+                } else if (i - prev > 1) {
+                    bridge(prev, vprev, i, v);
+                }
+                os[(int64_t)i * C] = v;
+                prev = i;
+                vprev = v;
+            }
+        }
+    }
+    if (prev < 0) {                         // :19-21 nothing observed: the zero path
+        for (int i = 0; i < L; ++i) os[(int64_t)i * C] = T(0);
+    } else if (prev < L - 1) {              // :33-34 the last entry takes the last observation
+        os[(int64_t)(L - 1) * C] = vprev;
+        bridge(prev, vprev, L - 1, vprev);
+    }
+}
+
+// misc.forward_fill (misc.py:103-126) and _prepare_rectilinear_interpolation
+// (interpolation_linear.py:87-128).  RECT = false: out has L rows; RECT = true: 2L-1 rows, row
+// 2i = held[i], row 2i+1 = held[i] except the time channel which takes held[i+1].
+template <typename T, bool RECT>
+__global__ void __launch_bounds__(kThreads)
+hold_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n_series, int L, int C, int time_index,
+            int32_t* __restrict__ flags) {
+    const int64_t g = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    if (g >= n_series) return;
+    const int64_t p = g / C;
+    const int c = (int)(g - p * C);
+    const T* xs = x + p * L * C + c;
+    const int out_rows = RECT ? 2 * L - 1 : L;
+    T* os = out + p * out_rows * C + c;
+    const bool is_time = RECT && (c == time_index);
+    int32_t seen = 0;
+    T held = xs[0];
+    if (is_nan(held)) seen |= TCDE_FLAG_NAN_SEEN | TCDE_FLAG_NAN_FIRST_ROW | (is_time ? TCDE_FLAG_NAN_TIME : 0);
+    for (int i0 = 0; i0 < L; i0 += 8) {
+        T ahead[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ahead[k] = (i0 + k < L) ? xs[(int64_t)(i0 + k) * C] : T(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k;
+            if (i < L) {
+                const T v = ahead[k];
+                const T before = held;
+                if (!is_nan(v)) held = v;
+                else seen |= TCDE_FLAG_NAN_SEEN | (is_time ? TCDE_FLAG_NAN_TIME : 0);
+                if (RECT) {
+                    if (i > 0) os[(int64_t)(2 * i - 1) * C] = is_time ? held : before;
+                    os[(int64_t)(2 * i) * C] = held;
+                } else {
+                    os[(int64_t)i * C] = held;
+                }
+            }
+        }
+    }
+    if (seen && flags != nullptr) atomicOr(flags, seen);
+}
+
+// =========================================================================================
+// Natural cubic spline, NaN-free knots  (interpolation_cubic.py:7-53, misc.py:13-67)
+// =========================================================================================
+// The knots are shared by the whole batch (misc.py:83), so the eliminated diagonal and the
+// forward multipliers of the Thomas solve are batch independent: one tiny kernel forms them
+// once (the reference recomputes them for every series).  workspace = [rdt | rdt2 | mult | rnd].
+template <typename T>
+__global__ void natural_prep_kernel(const T* __restrict__ t, T* __restrict__ ws, int L) {
+    using E = exact<T>;
+    T* rdt = ws;
+    T* rdt2 = ws + L;
+    T* mult = ws + 2 * L;
+    T* rnd = ws + 3 * L;
+    for (int i = threadIdx.x; i < L - 1; i += blockDim.x) {
+        const T t0 = t ? t[i] : T(i), t1 = t ? t[i + 1] : T(i + 1);
+        const T r = E::div(T(1), E::sub(t1, t0));
+        rdt[i] = r;
+        rdt2[i] = E::mul(r, r);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rdt[L - 1] = T(0);
+        rdt2[L - 1] = T(0);
+        // diag[i] = 2 * (rdt[i] + rdt[i-1]) with the out-of-range terms absent (cubic.py:31-35)
+        T nd = E::mul(T(2), rdt[0]);
+        // mult[0] is unused by the sweep; it carries t1 - t0 for the two-knot case (cubic.py:18)
+        mult[0] = E::sub(t ? t[1] : T(1), t ? t[0] : T(0));
+        rnd[0] = E::div(T(1), nd);
+        for (int i = 1; i < L; ++i) {
+            const T diag = E::mul(T(2), (i < L - 1) ? E::add(rdt[i], rdt[i - 1]) : E::add(T(0), rdt[i - 1]));
+            const T w = E::div(rdt[i - 1], nd);                  // misc.py:59
+            nd = E::sub(diag, E::mul(w, rdt[i - 1]));            // misc.py:60
+            mult[i] = w;
+            rnd[i] = E::div(T(1), nd);
+        }
+    }
+}
+
+// One CTA per group of S paths.  Phase 1: coalesced load, transposed into shared memory as
+// [series][knot] so that the thread that owns a series walks contiguous words.  Phase 2: one
+// thread per series runs the forward sweep and the back substitution in shared memory.
+// Phase 3: all threads turn (x, slope) into the [a|b|2c|3d] rows, staged per tile and written
+// with bulk stores exactly like the Hermite kernel.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+natural_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restrict__ out, int64_t n_paths, int L, int C,
+               int S, int Lp, int TR, int use_bulk, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using E = exact<T>;
+    const int row_elems = 4 * C;
+    const int path_stride = C * Lp + 1;
+    T* ot0 = reinterpret_cast<T*>(smem_raw);
+    T* ot1 = ot0 + (size_t)TR * row_elems;
+    T* rdt = ot1 + (size_t)TR * row_elems;
+    T* rdt2 = rdt + L;
+    T* mult = rdt2 + L;
+    T* rnd = mult + L;
+    T* xs = rnd + L;
+    T* ks = xs + (size_t)S * path_stride;
+
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 4 * L; e += kThreads) rdt[e] = ws[e];
+    bool saw_nan = false;
+    int buf = 0;
+    const int64_t n_groups = (n_paths + S - 1) / S;
+    const int di = kThreads / C, dc = kThreads - di * C;
+
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t p0 = grp * S;
+        const int np = (int)min((int64_t)S, n_paths - p0);
+        __syncthreads();   // previous group's phase 3 is done with xs / ks
+        {
+            const T* xg = x + p0 * L * C;
+            int i = tid / C, c = tid - (tid / C) * C, p = 0;
+            while (i >= L) { i -= L; ++p; }
+            const int total = np * L * C;
+            for (int e = tid; e < total; e += kThreads) {
+                const T v = xg[e];
+                saw_nan |= is_nan(v);
+                xs[p * path_stride + c * Lp + i] = v;
+                i += di;
+                c += dc;
+                if (c >= C) { c -= C; ++i; }
+                while (i >= L) { i -= L; ++p; }
+            }
+        }
+        __syncthreads();
+        if (tid < np * C && L > 2) {
+            const int p = tid / C, c = tid - p * C;
+            const T* xr = xs + p * path_stride + c * Lp;
+            T* kr = ks + p * path_stride + c * Lp;
+            // forward sweep (misc.py:58-61); rhs[i] = scaled[i] + scaled[i-1] (cubic.py:36-39)
+            T x_lo = xr[0], x_hi = xr[1];
+            T scaled_prev = E::mul(E::mul(T(3), E::sub(x_hi, x_lo)), rdt2[0]);
+            T f = scaled_prev;
+            kr[0] = f;
+            for (int i = 1; i < L; ++i) {
+                T rhs;
+                if (i < L - 1) {
+                    x_lo = x_hi;
+                    x_hi = xr[i + 1];
+                    const T scaled = E::mul(E::mul(T(3), E::sub(x_hi, x_lo)), rdt2[i]);
+                    rhs = E::add(scaled, scaled_prev);
+                    scaled_prev = scaled;
+                } else {
+                    rhs = E::add(T(0), scaled_prev);
+                }
+                f = E::sub(rhs, E::mul(mult[i], f));
+                kr[i] = f;
+            }
+            // back substitution (misc.py:63-65), dividing by nd as a multiplication by 1/nd
+            T k = E::mul(f, rnd[L - 1]);
+            kr[L - 1] = k;
+            for (int i = L - 2; i >= 0; --i) {
+                k = E::mul(E::sub(kr[i], E::mul(rdt[i], k)), rnd[i]);
+                kr[i] = k;
+            }
+        }
+        __syncthreads();
+        // phase 3
+        for (int p = 0; p < np; ++p) {
+            for (int r0 = 0; r0 < L - 1; r0 += TR, buf ^= 1) {
+                const int nr = min(TR, L - 1 - r0);
+                if (use_bulk && tid == 0) bulk_wait_read<1>();
+                __syncthreads();
+                T* ot = buf ? ot1 : ot0;
+                int i = tid / C, c = tid - (tid / C) * C;
+                for (int e = tid; e < nr * C; e += kThreads) {
+                    const int r = r0 + i;
+                    const T* xr = xs + p * path_stride + c * Lp + r;
+                    const T* kr = ks + p * path_stride + c * Lp + r;
+                    const T xl = xr[0], xh = xr[1];
+                    T b, two_c, three_d;
+                    if (L == 2) {                       // cubic.py:16-20
+                        b = E::div(E::sub(xh, xl), mult[0]);
+                        two_c = T(0);
+                        three_d = T(0);
+                    } else {
+                        const T kl = kr[0], kh = kr[1];
+                        const T six = E::mul(T(2), E::mul(T(3), E::sub(xh, xl)));
+                        const T sr = E::mul(six, rdt[r]);
+                        b = kl;
+                        two_c = E::mul(E::sub(E::sub(sr, E::mul(T(4), kl)), E::mul(T(2), kh)), rdt[r]);      // :45-47
+                        three_d = E::mul(E::add(-sr, E::mul(T(3), E::add(kl, kh))), rdt2[r]);                // :48-50
+                    }
+                    T* row = ot + (size_t)i * row_elems + c;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int w = (k + i) & 3;
+                        const T v = (w == 0) ? xl : (w == 1) ? b : (w == 2) ? two_c : three_d;
+                        row[w * C] = v;
+                    }
+                    i += di;
+                    c += dc;
+                    if (c >= C) { c -= C; ++i; }
+                }
+                T* gp = out + ((p0 + p) * (int64_t)(L - 1) + r0) * row_elems;
+                if (use_bulk) {
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    if (tid == 0) {
+                        bulk_store(gp, ot, (uint32_t)((size_t)nr * row_elems * sizeof(T)));
+                        bulk_commit();
+                    }
+                } else {
+                    __syncthreads();
+                    for (int e = tid; e < nr * row_elems; e += kThreads) gp[e] = ot[e];
+                }
+            }
+        }
+    }
+    if (use_bulk && tid == 0) bulk_wait_read<0>();
+    if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
+}
+
+// =========================================================================================
+// Natural cubic spline with missing values, one thread per series  (cubic.py:56-167)
+// =========================================================================================
+// Irregular path: each series has its own set of observed knots, so the tridiagonal system
+// differs per series.  scratch holds, per series, 3 rows of length L in a [row][knot][series]
+// layout (coalesced across the warp): compacted rhs/solution, eliminated diagonal, and the
+// knot slopes.  Exact arithmetic (the reference order) throughout.
+template <typename T, bool UNIT>
+__global__ void __launch_bounds__(128)
+natural_missing_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, T* __restrict__ scratch,
+                       int64_t n_series, int L, int C, int version) {
+    using E = exact<T>;
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_series) return;
+    const int64_t p = g / C;
+    const int c = (int)(g - p * C);
+    const T* xs = x + p * L * C + c;
+    T* os = out + p * (int64_t)(L - 1) * 4 * C + c;
+    auto time_of = [&](int i) -> T { return UNIT ? T(i) : t[i]; };
+    // scratch rows, element (row, j) of this series at scratch[(row * L + j) * n_series + g]
+    auto S0 = [&](int j) -> T& { return scratch[((int64_t)0 * L + j) * n_series + g]; };   // rhs -> fwd -> slope
+    auto S1 = [&](int j) -> T& { return scratch[((int64_t)1 * L + j) * n_series + g]; };   // eliminated diagonal
+    auto S2 = [&](int j) -> T& { return scratch[((int64_t)2 * L + j) * n_series + g]; };   // compacted value
+    auto S3 = [&](int j) -> T& { return scratch[((int64_t)3 * L + j) * n_series + g]; };   // compacted time
+
+    // first / last observation
+    int first = -1, last = -1;
+    for (int i = 0; i < L; ++i) {
+        if (!is_nan(xs[(int64_t)i * C])) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    }
+    const int rows = L - 1;
+    if (first < 0) {                                             // cubic.py:85-92
+        for (int i = 0; i < rows; ++i)
+            for (int w = 0; w < 4; ++w) os[((int64_t)i * 4 + w) * C] = T(0);
+        return;
+    }
+    const T vfirst = xs[(int64_t)first * C], vlast = xs[(int64_t)last * C];
+    // compact the (imputed) observed knots: cubic.py:101-133
+    int m = 0;
+    for (int i = 0; i < L; ++i) {
+        T v = xs[(int64_t)i * C];
+        if (is_nan(v)) {
+            if (version == 0) {
+                if (i == 0) v = vfirst;
+                else if (i == L - 1) v = vlast;
+            } else {
+                if (i < first) v = vfirst;
+                else if (i > last) v = vlast;
+            }
+        }
+        if (!is_nan(v)) {
+            S2(m) = v;
+            S3(m) = time_of(i);
+            ++m;
+        }
+    }
+    // m >= 2 always (both ends are observed after imputation)
+    if (m > 2) {
+        // system of cubic.py:23-39 on the compacted knots, Thomas solve of misc.py:52-65
+        T rprev = E::div(T(1), E::sub(S3(1), S3(0)));
+        T scaled_prev = E::mul(E::mul(T(3), E::sub(S2(1), S2(0))), E::mul(rprev, rprev));
+        T nd = E::mul(T(2), rprev);
+        T f = scaled_prev;
+        S0(0) = f;
+        S1(0) = nd;
+        for (int j = 1; j < m; ++j) {
+            T diag, rhs, rcur = T(0);
+            if (j < m - 1) {
+                rcur = E::div(T(1), E::sub(S3(j + 1), S3(j)));
+                const T scaled = E::mul(E::mul(T(3), E::sub(S2(j + 1), S2(j))), E::mul(rcur, rcur));
+                diag = E::mul(T(2), E::add(rcur, rprev));
+                rhs = E::add(scaled, scaled_prev);
+                scaled_prev = scaled;
+            } else {
+                diag = E::mul(T(2), E::add(T(0), rprev));
+                rhs = E::add(T(0), scaled_prev);
+            }
+            const T w = E::div(rprev, nd);
+            nd = E::sub(diag, E::mul(w, rprev));
+            f = E::sub(rhs, E::mul(w, f));
+            S0(j) = f;
+            S1(j) = nd;
+            rprev = rcur;
+        }
+        T k = E::div(f, nd);
+        S0(m - 1) = k;
+        for (int j = m - 2; j >= 0; --j) {
+            const T up = E::div(T(1), E::sub(S3(j + 1), S3(j)));
+            k = E::div(E::sub(S0(j), E::mul(up, k)), S1(j));
+            S0(j) = k;
+        }
+    }
+    // walk the original intervals; piece q spans compacted knots q, q+1   (cubic.py:147-162)
+    int q = -1;
+    T pa = T(0), pb = T(0), pc = T(0), pd = T(0), anchor = T(0);
+    int next_obs = 0;   // index into compacted knots of the next observed time
+    for (int i = 0; i < rows; ++i) {
+        const T ti = time_of(i);
+        if (next_obs < m && ti >= S3(next_obs)) {
+            q = next_obs;
+            ++next_obs;
+            anchor = S3(q);
+            const T xl = S2(q), xh = S2(q + 1);
+            if (m == 2) {                                        // cubic.py:16-20
+                pa = xl;
+                pb = E::div(E::sub(xh, xl), E::sub(S3(1), S3(0)));
+                pc = T(0);
+                pd = T(0);
+            } else {
+                const T r = E::div(T(1), E::sub(S3(q + 1), S3(q)));
+                const T r2 = E::mul(r, r);
+                const T kl = S0(q), kh = S0(q + 1);
+                const T six = E::mul(T(2), E::mul(T(3), E::sub(xh, xl)));
+                const T sr = E::mul(six, r);
+                pa = xl;
+                pb = kl;
+                pc = E::mul(E::sub(E::sub(sr, E::mul(T(4), kl)), E::mul(T(2), kh)), r);
+                pd = E::mul(E::add(-sr, E::mul(T(3), E::add(kl, kh))), r2);
+            }
+        }
+        const T off = E::sub(anchor, ti);
+        const T inner = E::mul(E::sub(E::mul(T(0.5), pc), E::div(E::mul(pd, off), T(3))), off);
+        os[((int64_t)i * 4 + 0) * C] = E::add(pa, E::mul(E::sub(inner, pb), off));
+        os[((int64_t)i * 4 + 1) * C] = E::add(pb, E::mul(E::sub(E::mul(pd, off), pc), off));
+        os[((int64_t)i * 4 + 2) * C] = E::sub(pc, E::mul(E::mul(T(2), pd), off));
+        os[((int64_t)i * 4 + 3) * C] = pd;
+    }
+}
+
+// torch.isnan(x).any() of interpolation_linear.py:169 as one pass that only sets a flag.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+nan_flag_kernel(const T* __restrict__ x, int64_t n, int32_t* __restrict__ flags) {
+    bool seen = false;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += stride) seen |= is_nan(x[i]);
+    if (__syncthreads_or(seen) && threadIdx.x == 0) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
+}
+
+// =========================================================================================
+// launchers
+// =========================================================================================
+static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t n_items) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int64_t g = (int64_t)sm_count() * per_sm;
+    if (g > n_items) g = n_items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static constexpr size_t kMaxSmem = 200 * 1024;
+
+template <typename T>
+static int launch_hermite(const T* x, const T* t, T* out, int64_t n_paths, int L, int C, int32_t* flags,
+                          cudaStream_t stream) {
+    const size_t row_bytes = (size_t)4 * C * sizeof(T);
+    int TR = (int)(16384 / row_bytes);
+    if (TR < 1) TR = 1;
+    if (TR > L - 1) TR = L - 1;
+    const size_t smem = 2 * TR * row_bytes + (size_t)(TR + 2) * C * sizeof(T) + (size_t)(TR + 2) * sizeof(T) + 16;
+    TCDE_CHECK_SUPPORTED(smem <= kMaxSmem, "hermite: channels=%d needs %zu bytes of shared memory (max %zu)", C, smem,
+                         kMaxSmem);
+    const int tiles = (L - 1 + TR - 1) / TR;
+    const int use_bulk = aligned16(out) ? 1 : 0;
+    auto kern = t ? hermite_kernel<T, false> : hermite_kernel<T, true>;
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = persistent_grid((const void*)kern, kThreads, smem, n_paths * tiles);
+    kern<<<grid, kThreads, smem, stream>>>(x, t, out, n_paths, L, C, TR, tiles, use_bulk, flags);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+template <typename T>
+static int launch_natural(const T* x, const T* t, T* out, T* ws, int64_t n_paths, int L, int C, int32_t* flags,
+                          cudaStream_t stream) {
+    natural_prep_kernel<T><<<1, 128, 0, stream>>>(t, ws, L);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    const size_t row_bytes = (size_t)4 * C * sizeof(T);
+    int TR = (int)(8192 / row_bytes);
+    if (TR < 1) TR = 1;
+    if (TR > L - 1) TR = L - 1;
+    int cp = 1;
+    while (cp < C && cp < 32) cp <<= 1;
+    const int Lp = ((L + 31) / 32) * 32 + 32 / cp;
+    const size_t per_path = (size_t)2 * ((size_t)C * Lp + 1) * sizeof(T);
+    const size_t fixed = 2 * TR * row_bytes + (size_t)4 * L * sizeof(T) + 16;
+    int S = (32 + C - 1) / C;
+    while (S > 1 && fixed + S * per_path > 100 * 1024) --S;
+    const size_t smem = fixed + S * per_path;
+    TCDE_CHECK_SUPPORTED(smem <= kMaxSmem,
+                         "natural cubic: length=%d x channels=%d needs %zu bytes of shared memory (max %zu)", L, C,
+                         smem, kMaxSmem);
+    const int use_bulk = aligned16(out) ? 1 : 0;
+    auto kern = natural_kernel<T>;
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_groups = (n_paths + S - 1) / S;
+    const int grid = persistent_grid((const void*)kern, kThreads, smem, n_groups);
+    kern<<<grid, kThreads, smem, stream>>>(x, ws, out, n_paths, L, C, S, Lp, TR, use_bulk, flags);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+static int check_shape(const void* x, const void* out, int64_t n_paths, int64_t length, int64_t channels, int dtype) {
+    TCDE_CHECK_ARG(x != nullptr && out != nullptr, "null data pointer");
+    TCDE_CHECK_ARG(n_paths >= 0 && channels >= 1, "n_paths=%lld channels=%lld", (long long)n_paths,
+                   (long long)channels);
+    TCDE_CHECK_ARG(length >= 2, "length=%lld (need at least 2 knots, misc.py:96-98)", (long long)length);
+    TCDE_CHECK_ARG(dtype == TCDE_F32 || dtype == TCDE_F64, "dtype=%d", dtype);
+    TCDE_CHECK_SUPPORTED(length < (1 << 24) && channels < (1 << 20), "length / channels too large");
+    return TCDE_OK;
+}
+
+}  // namespace tcde
+
+using namespace tcde;
+
+extern "C" int tcde_hermite_bdiff_coeffs(const void* x, const void* t, void* coeffs, int64_t n_paths, int64_t length,
+                                         int64_t channels, int dtype, int32_t* flags, void* stream) {
+    int rc = check_shape(x, coeffs, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    if (n_paths == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TCDE_F32)
+        return launch_hermite<float>((const float*)x, (const float*)t, (float*)coeffs, n_paths, (int)length,
+                                     (int)channels, flags, s);
+    return launch_hermite<double>((const double*)x, (const double*)t, (double*)coeffs, n_paths, (int)length,
+                                  (int)channels, flags, s);
+}
+
+extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t n_paths, int64_t length,
+                                int64_t channels, int dtype, void* stream) {
+    int rc = check_shape(x, out, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    const int64_t n_series = n_paths * channels;
+    if (n_series == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t blocks = (n_series + kThreads - 1) / kThreads;
+    TCDE_CHECK_SUPPORTED(blocks < (1ll << 31), "too many series");
+    const int L = (int)length, C = (int)channels;
+    if (dtype == TCDE_F32) {
+        if (t) linear_fill_kernel<float, false><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, (const float*)t, (float*)out, n_series, L, C);
+        else linear_fill_kernel<float, true><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, nullptr, (float*)out, n_series, L, C);
+    } else {
+        if (t) linear_fill_kernel<double, false><<<(unsigned)blocks, kThreads, 0, s>>>((const double*)x, (const double*)t, (double*)out, n_series, L, C);
+        else linear_fill_kernel<double, true><<<(unsigned)blocks, kThreads, 0, s>>>((const double*)x, nullptr, (double*)out, n_series, L, C);
+    }
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+template <bool RECT>
+static int launch_hold(const void* x, void* out, int64_t n_paths, int64_t length, int64_t channels, int64_t time_index,
+                       int dtype, int32_t* flags, void* stream) {
+    int rc = check_shape(x, out, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    if (RECT) TCDE_CHECK_ARG(time_index >= 0 && time_index < channels, "time_index=%lld", (long long)time_index);
+    const int64_t n_series = n_paths * channels;
+    if (n_series == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t blocks = (n_series + kThreads - 1) / kThreads;
+    TCDE_CHECK_SUPPORTED(blocks < (1ll << 31), "too many series");
+    if (dtype == TCDE_F32)
+        hold_kernel<float, RECT><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, (float*)out, n_series, (int)length, (int)channels, (int)time_index, flags);
+    else
+        hold_kernel<double, RECT><<<(unsigned)blocks, kThreads, 0, s>>>((const double*)x, (double*)out, n_series, (int)length, (int)channels, (int)time_index, flags);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+extern "C" int tcde_forward_fill(const void* x, void* out, int64_t n_paths, int64_t length, int64_t channels,
+                                 int dtype, int32_t* flags, void* stream) {
+    return launch_hold<false>(x, out, n_paths, length, channels, 0, dtype, flags, stream);
+}
+
+extern "C" int tcde_rectilinear_prepare(const void* x, void* out, int64_t n_paths, int64_t length, int64_t channels,
+                                        int64_t time_index, int dtype, int32_t* flags, void* stream) {
+    return launch_hold<true>(x, out, n_paths, length, channels, time_index, dtype, flags, stream);
+}
+
+extern "C" int tcde_natural_cubic_coeffs(const void* x, const void* t, void* coeffs, void* workspace, int64_t n_paths,
+                                         int64_t length, int64_t channels, int dtype, int32_t* flags, void* stream) {
+    int rc = check_shape(x, coeffs, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    TCDE_CHECK_ARG(workspace != nullptr, "null workspace");
+    if (n_paths == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == TCDE_F32)
+        return launch_natural<float>((const float*)x, (const float*)t, (float*)coeffs, (float*)workspace, n_paths,
+                                     (int)length, (int)channels, flags, s);
+    return launch_natural<double>((const double*)x, (const double*)t, (double*)coeffs, (double*)workspace, n_paths,
+                                  (int)length, (int)channels, flags, s);
+}
+
+extern "C" int64_t tcde_natural_cubic_missing_scratch_bytes(int64_t n_paths, int64_t length, int64_t channels,
+                                                            int dtype) {
+    const int64_t elem = (dtype == TCDE_F64) ? 8 : 4;
+    return 4 * length * n_paths * channels * elem;
+}
+
+extern "C" int tcde_natural_cubic_coeffs_missing(const void* x, const void* t, void* coeffs, void* scratch,
+                                                 int64_t n_paths, int64_t length, int64_t channels, int version,
+                                                 int dtype, void* stream) {
+    int rc = check_shape(x, coeffs, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    TCDE_CHECK_ARG(scratch != nullptr, "null scratch");
+    TCDE_CHECK_ARG(version == 0 || version == 1, "version=%d", version);
+    const int64_t n_series = n_paths * channels;
+    if (n_series == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int threads = 128;
+    const int64_t blocks = (n_series + threads - 1) / threads;
+    TCDE_CHECK_SUPPORTED(blocks < (1ll << 31), "too many series");
+    const int L = (int)length, C = (int)channels;
+    if (dtype == TCDE_F32) {
+        if (t) natural_missing_kernel<float, false><<<(unsigned)blocks, threads, 0, s>>>((const float*)x, (const float*)t, (float*)coeffs, (float*)scratch, n_series, L, C, version);
+        else natural_missing_kernel<float, true><<<(unsigned)blocks, threads, 0, s>>>((const float*)x, nullptr, (float*)coeffs, (float*)scratch, n_series, L, C, version);
+    } else {
+        if (t) natural_missing_kernel<double, false><<<(unsigned)blocks, threads, 0, s>>>((const double*)x, (const double*)t, (double*)coeffs, (double*)scratch, n_series, L, C, version);
+        else natural_missing_kernel<double, true><<<(unsigned)blocks, threads, 0, s>>>((const double*)x, nullptr, (double*)coeffs, (double*)scratch, n_series, L, C, version);
+    }
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+extern "C" int tcde_nan_flag(const void* x, int64_t n, int dtype, int32_t* flags, void* stream) {
+    TCDE_CHECK_ARG(x != nullptr && flags != nullptr && n >= 0, "null pointer or negative size");
+    TCDE_CHECK_ARG(dtype == TCDE_F32 || dtype == TCDE_F64, "dtype=%d", dtype);
+    if (n == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int64_t blocks = (n + kThreads * 8 - 1) / (kThreads * 8);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == TCDE_F32) nan_flag_kernel<float><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, n, flags);
+    else nan_flag_kernel<double><<<(unsigned)blocks, kThreads, 0, s>>>((const double*)x, n, flags);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}

@@ -1,0 +1,93 @@
+// Shared device/host helpers for the torchcde_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/torchcde_b200.h"
+
+namespace tcde {
+
+// ---- error plumbing (nothing throws across the C ABI) ------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_failed(cudaError_t e, const char* what);
+
+#define TCDE_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            tcde::set_error(__VA_ARGS__);         \
+            return TCDE_ERR_ARGUMENT;             \
+        }                                         \
+    } while (0)
+
+#define TCDE_CHECK_SUPPORTED(cond, ...)           \
+    do {                                          \
+        if (!(cond)) {                            \
+            tcde::set_error(__VA_ARGS__);         \
+            return TCDE_ERR_UNSUPPORTED;          \
+        }                                         \
+    } while (0)
+
+#define TCDE_CHECK_CUDA(call)                                         \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return tcde::cuda_failed(e_, #call);   \
+    } while (0)
+
+int sm_count();
+
+// ---- arithmetic that must round exactly once per operation --------------------------------
+// The reference is a chain of separate torch elementwise ops, i.e. one IEEE rounding per
+// +,-,*,/ and never a fused multiply-add.  Kernels that promise bit-identical results use
+// these wrappers so that nvcc cannot contract a*b+c into an FMA.
+template <typename T> struct exact;
+template <> struct exact<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct exact<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }
+
+// ---- 1-D bulk (TMA) shared -> global store -------------------------------------------------
+// cp.async.bulk moves a contiguous, 16-byte-aligned byte range with one instruction issued by
+// one thread; SASS shows it as UBLKCP.  The async proxy must see the generic-proxy writes to
+// shared memory first, hence the proxy fence before the CTA barrier that precedes the issue.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem, const void* smem, uint32_t bytes) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ---- 16-byte cp.async (LDGSTS) global -> shared --------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace tcde

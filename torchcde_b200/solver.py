@@ -1,0 +1,353 @@
+"""``cdeint`` -- the host side of hot path (ii).
+
+Same signature, validation, exception types/messages, defaults and output layout as the
+reference adapter (torchcde/solver.py:144-245).  What differs is what happens where the
+reference leaves for torchdiffeq (solver.py:226-227): nothing is dispatched to torchdiffeq or
+torchsde.  For the fixed-step methods the whole solve -- spline derivative, vector field,
+contraction, Runge-Kutta combination, output interpolation -- is ONE launch of the fused
+kernel (``tcde_cdeint_fixed_linear``) when the vector field is the README-form linear map;
+any other ``func`` runs through this package's own on-GPU stage loop, which keeps the
+reference's arithmetic but issues no per-stage host syncs.
+"""
+import warnings
+import weakref
+
+import torch
+
+from . import _lib
+from .controls import CubicSpline, LinearInterpolation, _schedule_knots
+from .schedule import FIXED_METHODS, ScheduleCache, build_schedule
+
+_schedules = ScheduleCache()
+
+
+# ------------------------------------------------------------------------------ vector fields
+class LinearVectorField(torch.nn.Module):
+    """The README's vector field (README.md:42-49): ``Linear(H, H*C)(z).view(..., H, C)``.
+
+    ``cdeint`` recognises this class (and structurally identical user modules) and fuses it.
+    """
+
+    def __init__(self, hidden_channels, input_channels, bias=True, device=None, dtype=None):
+        super().__init__()
+        self.hidden_channels = hidden_channels
+        self.input_channels = input_channels
+        self.linear = torch.nn.Linear(hidden_channels, hidden_channels * input_channels, bias=bias, device=device,
+                                      dtype=dtype)
+
+    def forward(self, t, z):
+        return self.linear(z).view(*z.shape[:-1], self.hidden_channels, self.input_channels)
+
+
+_recognised = weakref.WeakKeyDictionary()
+
+
+def _single_linear(func):
+    """The one ``nn.Linear`` of ``func`` if ``func`` consists of nothing else, otherwise None."""
+    if not isinstance(func, torch.nn.Module) or hasattr(func, "prod"):
+        return None
+    mods = [m for m in func.modules() if m is not func]
+    if len(mods) != 1 or not isinstance(mods[0], torch.nn.Linear):
+        return None
+    if len(list(func.parameters())) != len(list(mods[0].parameters())) or len(list(func.buffers())) != 0:
+        return None
+    return mods[0]
+
+
+def linear_field_of(func, z0, channels, t0):
+    """Return ``(weight, bias)`` if ``func(t, z)`` is exactly ``Linear(H, H*C)(z).view(..., H, C)``.
+
+    ``LinearVectorField`` is trusted; any other module made of a single ``nn.Linear`` of the
+    right shape is *probed* on a handful of paths and must reproduce the linear map bit for
+    bit (so a module that adds an activation is never mistaken for a linear field)."""
+    hidden = z0.size(-1)
+    if isinstance(func, LinearVectorField):
+        lin = func.linear
+        if lin.in_features == hidden and lin.out_features == hidden * channels:
+            return lin.weight, lin.bias
+        return None
+    lin = _single_linear(func)
+    if lin is None or lin.in_features != hidden or lin.out_features != hidden * channels:
+        return None
+    try:
+        known = _recognised.get(func)
+    except TypeError:
+        known = None
+    if known is None:
+        known = _probe(func, lin, z0, channels, t0)
+        try:
+            _recognised[func] = known
+        except TypeError:
+            pass
+    return (lin.weight, lin.bias) if known else None
+
+
+def _probe(func, lin, z0, channels, t0):
+    hidden = z0.size(-1)
+    with torch.no_grad():
+        flat = z0.detach().reshape(-1, hidden)
+        small = z0.detach() if flat.size(0) * hidden * channels <= (1 << 22) else None
+        candidates = [small] if small is not None else [z0.detach()[tuple(slice(0, 1) for _ in z0.shape[:-1])]]
+        for zp in candidates:
+            try:
+                got = func(t0, zp)
+            except Exception:
+                warnings.warn("torchcde_b200.cdeint: `func` looks like a single nn.Linear but could not be probed on "
+                              "a slice of z0 (does it hard-code the batch size?). Falling back to the generic stage "
+                              "loop; use torchcde_b200.LinearVectorField to get the fused kernel.")
+                return False
+            want = torch.nn.functional.linear(zp, lin.weight, lin.bias).view(*zp.shape[:-1], hidden, channels)
+            if not (isinstance(got, torch.Tensor) and got.shape == want.shape and torch.equal(got, want)):
+                return False
+    return True
+
+
+# ------------------------------------------------------------------------------- validation
+def _shape_error_base(control_shape, z0):
+    if control_shape[:-1] != z0.shape[:-1]:
+        raise ValueError("X.derivative did not return a tensor with the same number of batch dimensions as z0. "
+                         "X.derivative returned shape {} (meaning {} batch dimensions), whilst z0 has shape {} "
+                         "(meaning {} batch dimensions)."
+                         "".format(tuple(control_shape), tuple(control_shape[:-1]), tuple(z0.shape),
+                                   tuple(z0.shape[:-1])))
+
+
+def _shape_error_forward(control_shape, system_shape, z0):
+    _shape_error_base(control_shape, z0)
+    if system_shape[:-2] != z0.shape[:-1]:
+        raise ValueError("func did not return a tensor with the same number of batch dimensions as z0. func returned "
+                         "shape {} (meaning {} batch dimensions), whilst z0 has shape {} (meaning {} batch"
+                         " dimensions)."
+                         "".format(tuple(system_shape), tuple(system_shape[:-2]), tuple(z0.shape),
+                                   tuple(z0.shape[:-1])))
+    if system_shape[-2] != z0.size(-1):
+        raise ValueError("func did not return a tensor with the same number of hidden channels as z0. func returned "
+                         "shape {} (meaning {} channels), whilst z0 has shape {} (meaning {} channels)."
+                         "".format(tuple(system_shape), system_shape[-2], tuple(z0.shape), z0.size(-1)))
+    if system_shape[-1] != control_shape[-1]:
+        raise ValueError("func did not return a tensor with the same number of input channels as X.derivative "
+                         "returned. func returned shape {} (meaning {} channels), whilst X.derivative returned shape "
+                         "{} (meaning {} channels)."
+                         "".format(tuple(system_shape), system_shape[-1], tuple(control_shape),
+                                   control_shape[-1]))
+
+
+def _shape_error_prod(control_shape, field_shape, z0):
+    _shape_error_base(control_shape, z0)
+    if field_shape != z0.shape:
+        raise ValueError("func.prod did not return a tensor with the same shape as z0. func.prod returned shape {} "
+                         "whilst z0 has shape {}."
+                         "".format(tuple(field_shape), tuple(z0.shape)))
+
+
+def _control_signature(X):
+    """(kind, batch shape, channels, n_intervals) of a built-in control without evaluating it."""
+    if isinstance(X, CubicSpline):
+        return _lib.CONTROL_CUBIC, tuple(X._b.shape[:-2]), X._b.size(-1), X._b.size(-2)
+    if isinstance(X, LinearInterpolation):
+        return _lib.CONTROL_LINEAR, tuple(X._coeffs.shape[:-2]), X._coeffs.size(-1), X._coeffs.size(-2) - 1
+    return None
+
+
+# --------------------------------------------------------------------------------- the solve
+def _fused_solve(X, weight, bias, z0, t, method, step_size):
+    kind, batch, channels, n_rows = _control_signature(X)
+    hidden = z0.size(-1)
+    dtype = z0.dtype
+    code = _lib.dtype_code(dtype)
+    control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+    for name, ten in (("the control's coefficients", control), ("func's weight", weight)):
+        if ten.dtype != dtype:
+            raise RuntimeError("torchcde_b200.cdeint: z0 is {} but {} are {}; they must match."
+                               .format(dtype, name, ten.dtype))
+    _lib.require_cuda(z0, control, weight)
+    with torch.cuda.device(z0.device):
+        control = control.detach().reshape(-1, control.size(-2), control.size(-1))
+        if not control.is_contiguous():
+            control = control.contiguous()
+        zf = z0.detach().reshape(-1, hidden).contiguous()
+        w = weight.detach().contiguous()
+        b = (bias.detach() if bias is not None else torch.zeros(hidden * channels, dtype=dtype, device=z0.device))
+        b = b.contiguous()
+        sched, (floats, ints, v) = _schedules.get(t, _schedule_knots(X), n_rows, method, step_size, dtype, z0.device)
+        out = torch.empty(zf.size(0), sched.n_out, hidden, dtype=dtype, device=z0.device)
+        _lib.call("tcde_cdeint_fixed_linear", _lib.ptr(control), kind, n_rows, _lib.ptr(w), _lib.ptr(b),
+                  _lib.ptr(zf), _lib.ptr(out), zf.size(0), channels, hidden, _lib.METHODS[method], sched.n_steps,
+                  _lib.ptr(v["step_dt"]), _lib.ptr(v["stage_index"]), _lib.ptr(v["stage_frac"]), sched.n_out,
+                  _lib.ptr(v["out_step"]), _lib.ptr(v["out_mode"]), _lib.ptr(v["out_slope"]), float(sched.sign), code,
+                  _lib.stream_of(zf))
+    return out.view(*z0.shape[:-1], sched.n_out, hidden)
+
+
+def _derivative_at(X, index, frac):
+    """dX/dt from a known interval (Python int) and fraction: the reference's arithmetic
+    (interpolation_cubic.py:331-336 / interpolation_linear.py:222-225) as differentiable torch
+    ops, without the 0-dim-tensor indexing that forces a host sync per stage."""
+    if isinstance(X, CubicSpline):
+        inner = X._two_c[..., index, :] + X._three_d[..., index, :] * frac
+        return X._b[..., index, :] + inner * frac
+    coeffs, knots = X._coeffs, X._t
+    return (coeffs[..., index + 1, :] - coeffs[..., index, :]) / (knots[index + 1] - knots[index])
+
+
+def _generic_solve(X, func, z0, t, method, step_size, is_prod, known_control):
+    """This package's own fixed-step driver for an arbitrary ``func`` / ``func.prod``
+    (solver.py:117-135 semantics): torch ops on the GPU, differentiable, one pass, no host
+    sync inside the time loop for the built-in controls."""
+    n_rows = _control_signature(X)[3] if known_control else None
+    dtype = z0.dtype
+    if known_control:
+        sched = build_schedule(t, _schedule_knots(X), n_rows, method, step_size, dtype)
+        idx = sched.stage_index.tolist()
+        frac_dev = sched.stage_frac.to(z0.device)
+    else:
+        sched = build_schedule(t, torch.zeros(2), 1, method, step_size, dtype)
+    times_dev = sched.stage_times.to(z0.device)
+    dts = sched.step_dt.to(z0.device)
+    slopes = sched.out_slope.to(z0.device)
+    sign = sched.sign
+
+    def field(i, s, z):
+        ts = times_dev[i, s]
+        if known_control:
+            dx = _derivative_at(X, idx[i][s], frac_dev[i, s])
+        else:
+            dx = X.derivative(ts)
+        if is_prod:
+            out = func.prod(ts, z, dx)
+        else:
+            out = (func(ts, z) @ dx.unsqueeze(-1)).squeeze(-1)
+        return out if sign > 0 else -1.0 * out
+
+    outs = [None] * sched.n_out
+    j = 0
+    while j < sched.n_out and int(sched.out_step[j]) < 0:
+        outs[j] = z0
+        j += 1
+    y = z0
+    third, two_thirds = 1 / 3, 2 / 3
+    for i in range(sched.n_steps):
+        dt = dts[i]
+        if method == "rk4":
+            k1 = field(i, 0, y)
+            k2 = field(i, 1, y + dt * k1 * third)
+            k3 = field(i, 2, y + dt * (k2 - k1 * third))
+            k4 = field(i, 3, y + dt * (k1 - k2 + k3))
+            y1 = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+        elif method == "midpoint":
+            k1 = field(i, 0, y)
+            y1 = y + dt * field(i, 1, y + k1 * (0.5 * dt))
+        else:
+            y1 = y + dt * field(i, 0, y)
+        while j < sched.n_out and int(sched.out_step[j]) == i:
+            mode = int(sched.out_mode[j])
+            if mode == 0:
+                outs[j] = y
+            elif mode == 1:
+                outs[j] = y1
+            else:
+                outs[j] = y + slopes[j] * (y1 - y)
+            j += 1
+        y = y1
+    return torch.stack(outs, dim=-2)
+
+
+def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
+    r"""Solves a system of controlled differential equations
+    ``z_t = z_{t_0} + \int_{t_0}^t f(s, z_s) dX_s``  (reference: torchcde/solver.py:144-245).
+
+    Arguments, defaults, errors and the returned layout ``(..., len(t), hidden_channels)`` follow
+    the reference.  ``**kwargs`` are the torchdiffeq keyword arguments the reference forwards
+    (``method``, ``options={'step_size': ...}``, ``rtol``, ``atol``, ``adjoint_*``).
+
+    Supported in this round: ``backend="torchdiffeq"`` semantics with the fixed-step methods
+    ``euler``, ``midpoint`` and ``rk4`` (torchdiffeq's 3/8 rule).  With a ``CubicSpline`` or
+    ``LinearInterpolation`` control and a linear ``func`` (``LinearVectorField`` or any module
+    that is exactly one ``nn.Linear`` + ``view``) the solve is one fused CUDA kernel; gradients
+    are served by the differentiable generic stage loop.
+    """
+    # Reduce the default values for the tolerances because CDEs are difficult to solve with the default high tolerances.
+    if 'atol' not in kwargs:
+        kwargs['atol'] = 1e-6
+    if 'rtol' not in kwargs:
+        kwargs['rtol'] = 1e-4
+    if adjoint:
+        if "adjoint_atol" not in kwargs:
+            kwargs["adjoint_atol"] = kwargs["atol"]
+        if "adjoint_rtol" not in kwargs:
+            kwargs["adjoint_rtol"] = kwargs["rtol"]
+
+    if not hasattr(X, 'derivative'):
+        raise ValueError("X must have a 'derivative' method.")
+    if isinstance(z0, (tuple, list)):
+        raise NotImplementedError("torchcde_b200.cdeint: tuple / list states (TupleControl) are outside the B200 hot "
+                                  "path; pass a single tensor state.")
+    if not isinstance(z0, torch.Tensor):
+        raise ValueError("z0 must either a tensor or a tuple/list of tensors.")
+    if backend == "torchsde":
+        raise NotImplementedError("torchcde_b200.cdeint: the torchsde backend is out of scope (SURVEY.md section 2, "
+                                  "row 8); use backend='torchdiffeq' semantics with a fixed-step method.")
+    if backend != "torchdiffeq":
+        raise ValueError(f"Unrecognised backend={backend}")
+
+    method = kwargs.get("method", None)
+    options = dict(kwargs.get("options", None) or {})
+    if method is None or method not in FIXED_METHODS:
+        raise NotImplementedError(
+            "torchcde_b200.cdeint: method={!r} is not built yet. This round implements torchdiffeq's fixed-step "
+            "methods {} (pass e.g. method='rk4', options={{'step_size': 1.0}}); the adaptive dopri5 default and its "
+            "adjoint are scheduled next (SURVEY.md section 7, step 7).".format(method, FIXED_METHODS))
+    step_size = options.pop("step_size", None)
+    if options:
+        raise NotImplementedError("torchcde_b200.cdeint: unsupported solver options {}".format(sorted(options)))
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+
+    is_prod = hasattr(func, 'prod')
+    sig = _control_signature(X)
+
+    if adjoint and 'adjoint_params' not in kwargs:
+        for buffer in X.buffers():
+            if buffer.requires_grad:
+                warnings.warn("One of the inputs to the control path X requires gradients but "
+                              "`kwargs['adjoint_params']` has not been passed. This is probably a mistake: these "
+                              "inputs will not receive a gradient when using the adjoint method. Either have the input "
+                              "not require gradients (if that was unintended), or include it (and every other "
+                              "parameter needing gradients) in `adjoint_params`. For example:\n"
+                              "```\n"
+                              "coeffs = ...\n"
+                              "func = ...\n"
+                              "X = CubicSpline(coeffs)\n"
+                              "adjoint_params = tuple(func.parameters()) + (coeffs,)\n"
+                              "cdeint(X=X, func=func, ..., adjoint_params=adjoint_params)\n"
+                              "```")
+
+    # ---- fused path: shapes are checked from metadata, nothing is evaluated on the batch ------
+    if sig is not None and not is_prod:
+        kind, batch, channels, _ = sig
+        t0 = t[0].detach().to(z0.dtype) if t.numel() else t
+        field = linear_field_of(func, z0, channels, t0)
+        if field is not None:
+            weight, bias = field
+            _shape_error_forward(batch + (channels,), tuple(z0.shape[:-1]) + (z0.size(-1), channels), z0)
+            wants_grad = torch.is_grad_enabled() and any(
+                x is not None and x.requires_grad for x in (z0, weight, bias, t, *X.buffers()))
+            if not wants_grad:
+                return _fused_solve(X, weight, bias, z0, t, method, step_size)
+
+    # ---- generic path: the reference's own compatibility check (solver.py:44-100), then our loop
+    _lib.require_cuda(z0)
+    control_gradient = X.derivative(t[0].detach())
+    if not isinstance(control_gradient, torch.Tensor):
+        raise ValueError("z0 is a tensor and so X.derivative must return a tensor as well.")
+    if is_prod:
+        vector_field = func.prod(t[0], z0, control_gradient)
+        if not isinstance(vector_field, torch.Tensor):
+            raise ValueError("z0 is a tensor and so func.prod must return a tensor as well.")
+        _shape_error_prod(tuple(control_gradient.shape), tuple(vector_field.shape), z0)
+    else:
+        system = func(t[0], z0)
+        if not isinstance(system, torch.Tensor):
+            raise ValueError("z0 is a tensor and so func must return a tensor as well.")
+        _shape_error_forward(tuple(control_gradient.shape), tuple(system.shape), z0)
+    return _generic_solve(X, func, z0, t, method, step_size, is_prod, sig is not None)
