@@ -35,6 +35,15 @@ FLOPS_PER_SEQ = 255 * (4 * (2 * HIDDEN * HIDDEN * CHANNELS + HIDDEN * CHANNELS +
 HERMITE_BYTES_PER_SEQ = LENGTH * CHANNELS * 4 + (LENGTH - 1) * 4 * CHANNELS * 4   # 40,832 B
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """Progress marker on stderr (the JSON line on stdout stays alone)."""
+    sys.stderr.write("[bench {:7.1f}s] {}\n".format(time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -134,10 +143,10 @@ def time_loop(fn, steps, warmup, device, dist=None):
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_solve_sample(sample_paths, threads):
-    """The reference's CPU path for the same workload: its op sequence (oracle port) on host cores."""
+def cpu_solve_sample(sample_paths):
+    """The reference's CPU path for the same workload: its op sequence (oracle port) on host cores,
+    with torch's default intra-op thread count (what a reference user gets)."""
     from oracle import cde_oracle as O
-    torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(sample_paths, LENGTH, CHANNELS, generator=gen).cumsum(1) / math.sqrt(LENGTH)
     z0 = torch.randn(sample_paths, HIDDEN, generator=gen)
@@ -153,28 +162,47 @@ def cpu_solve_sample(sample_paths, threads):
     return run
 
 
-def cpu_baseline(sample_paths=4096, reps=2):
-    threads = os.cpu_count() or 1
-    run = cpu_solve_sample(sample_paths, threads)
+def calibrated_sample(budget_s=8.0, lo=256, hi=8192):
+    """Pick the sample size so that one CPU solve takes about ``budget_s`` seconds."""
+    run = cpu_solve_sample(lo)
+    with torch.no_grad():
+        run()
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+    n = lo
+    while n * 2 <= hi and dt * (n * 2 / lo) <= budget_s:
+        n *= 2
+    note("cpu calibration: {} paths take {:.2f}s -> sample {}".format(lo, dt, n))
+    return n
+
+
+def cpu_baseline(reps=2):
+    threads = torch.get_num_threads()
+    sample_paths = calibrated_sample()
+    run = cpu_solve_sample(sample_paths)
     with torch.no_grad():
         run()
         t0 = time.perf_counter()
         for _ in range(reps):
             run()
         dt = (time.perf_counter() - t0) / reps
+    note("cpu baseline: {} paths in {:.2f}s".format(sample_paths, dt))
     return {"value": sample_paths / dt, "unit": "sequences/s", "cores": threads, "kind": "port",
+            "host_cpus": os.cpu_count(),
             "sample": "{} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's order "
-                      "(oracle/cde_oracle.py + oracle/odeint_port.py), mean of {} runs after 1 warm-up; "
-                      "torchdiffeq itself is not installable here".format(sample_paths, reps)}
+                      "(oracle/cde_oracle.py + oracle/odeint_port.py), mean of {} runs after 1 warm-up, torch's "
+                      "default {} intra-op threads; torchdiffeq itself is not installable here".format(
+                          sample_paths, reps, threads)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = 2048
-    run = cpu_solve_sample(sample, threads)
+    threads = torch.get_num_threads()
+    sample = calibrated_sample(budget_s=4.0)
+    run = cpu_solve_sample(sample)
     with torch.no_grad():
         for _ in range(args.warmup):
             run()
@@ -183,7 +211,7 @@ def run_reference_arm(args):
             run()
         total = time.perf_counter() - t0
     value = sample * args.steps / total
-    base = {"value": value, "unit": "sequences/s", "cores": threads, "kind": "port",
+    base = {"value": value, "unit": "sequences/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
             "sample": "each step = {} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's op "
                       "order (oracle port; torchdiffeq is not installable offline)".format(sample)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": args.gpus,
@@ -215,6 +243,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(device)
     _lib.load()
 
+    note("rank {} of {}: generating synthetic data".format(rank, world))
     x, z0, func = synthetic(BATCH, device, seed=1000 + rank)
     if dist is not None:
         from torchcde_b200.distributed import broadcast_field
@@ -229,6 +258,7 @@ def run_gpu_arm(args):
         def step():
             holder["out"] = cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options=options)
 
+        note("timing {} solves".format(args.steps))
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -236,6 +266,7 @@ def run_gpu_arm(args):
         clocks = sampler.stop() if rank == 0 else None
         assert bool(torch.isfinite(holder["out"]).all())
 
+        note("device-resident: {:.3f} ms per solve".format(ms / args.steps))
         # ---- end to end from pinned host buffers (copies inside the timed region) ------------
         coeffs_host = torch.empty(coeffs.shape, dtype=coeffs.dtype, pin_memory=True)
         coeffs_host.copy_(coeffs)
@@ -249,11 +280,13 @@ def run_gpu_arm(args):
             hostio.cdeint_from_host(coeffs_host, func, z0_host, t, out_host=out_host, chunk_paths=chunk,
                                     pipeline=pipe, device=device, method="rk4", options=options)
 
+        note("pinned host buffers ready; timing end to end")
         e2e_steps = max(2, min(args.steps, 5))
         e2e_ms = time_loop(e2e_step, e2e_steps, 1, device, dist)
         torch.cuda.synchronize(device)
         e2e_ok = torch.equal(out_host.to(device), holder["out"])
 
+        note("end to end: {:.3f} ms per solve, matches={}".format(e2e_ms / e2e_steps, bool(e2e_ok)))
         # ---- secondary kernels (rank 0, N=1 only): the HBM-bound coefficient builders ---------
         extra = {}
         if rank == 0:

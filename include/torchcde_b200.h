@@ -150,6 +150,11 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
                              double sign, int dtype, void* stream);
 
+/* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic choice,
+ * 1 = CUDA-core kernel (any shape), 2 = tcgen05 tensor-core kernel (hidden = 32, channels = 8;
+ * TCDE_ERR_UNSUPPORTED otherwise).  Process-wide; meant for tests and benchmarks. */
+TCDE_API int tcde_set_solve_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

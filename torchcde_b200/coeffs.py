@@ -73,6 +73,8 @@ def _flags(x):
 
 
 def _has_nan(flat):
+    if flat.numel() == 0:
+        return False
     flags = _flags(flat)
     _lib.call("tcde_nan_flag", _lib.ptr(flat), flat.numel(), _lib.dtype_code(flat.dtype), _lib.ptr(flags),
               _lib.stream_of(flat))
@@ -101,8 +103,9 @@ def forward_fill(x, fill_index=-2):
         out = torch.empty_like(flat)
         flags = _flags(flat)
         p, length, channels = flat.shape
-        _lib.call("tcde_forward_fill", _lib.ptr(flat), _lib.ptr(out), p, length, channels,
-                  _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
+        if flat.numel() > 0:
+            _lib.call("tcde_forward_fill", _lib.ptr(flat), _lib.ptr(out), p, length, channels,
+                      _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
     out = out.view(*batch, length, channels)
     return out.movedim(-2, fill_index) if moved is not x else out
 
@@ -176,6 +179,8 @@ def hermite_cubic_coefficients_with_backward_differences(x, t=None):
         code = _lib.dtype_code(flat.dtype)
         knots = None if t is None else _knots_arg(t_full, x)
         out = torch.empty(p, length - 1, 4 * channels, dtype=flat.dtype, device=flat.device)
+        if p == 0:
+            return out.view(*batch, length - 1, 4 * channels)
         flags = _flags(flat)
         stream = _lib.stream_of(flat)
         _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length, channels,
@@ -201,10 +206,18 @@ def _natural(x, t, version, name):
         out = torch.empty(p, length - 1, 4 * channels, dtype=flat.dtype, device=flat.device)
         flags = _flags(flat)
         stream = _lib.stream_of(flat)
+        if p == 0:
+            return out.view(*batch, length - 1, 4 * channels)
         workspace = torch.empty(4 * length, dtype=flat.dtype, device=flat.device)
-        _lib.call("tcde_natural_cubic_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), _lib.ptr(workspace),
-                  p, length, channels, code, _lib.ptr(flags), stream)
-        if flags.item() & _lib.FLAG_NAN_SEEN:
+        try:
+            _lib.call("tcde_natural_cubic_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out),
+                      _lib.ptr(workspace), p, length, channels, code, _lib.ptr(flags), stream)
+            per_series = bool(flags.item() & _lib.FLAG_NAN_SEEN)
+        except NotImplementedError:
+            # length x channels too large for the shared-memory kernel: the per-series kernel handles
+            # any shape (and NaN-free data just as well, in the reference's exact operation order)
+            per_series = True
+        if per_series:
             nbytes = _lib.load().tcde_natural_cubic_missing_scratch_bytes(p, length, channels, code)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
             _lib.call("tcde_natural_cubic_coeffs_missing", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out),

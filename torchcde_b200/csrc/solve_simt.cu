@@ -470,9 +470,29 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
     return TCDE_OK;
 }
 
+// ---- tensor-core variant (solve_umma.cu) -------------------------------------------------------
+struct UmmaArgs {
+    const float* control; const float* weight; const float* bias; const float* z0; float* out;
+    const float* step_dt; const int32_t* stage_index; const float* stage_frac;
+    const int32_t* out_step; const int32_t* out_mode; const float* out_slope;
+    int64_t n_paths; int64_t n_rows;
+    int control_kind, method, n_stages, n_steps, n_out;
+    float sign;
+};
+bool solve_umma_supported(int H, int C);
+int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
+
+static int g_solve_variant = 0;     // 0 = auto, 1 = CUDA-core kernel, 2 = tensor-core kernel
+
 }  // namespace tcde
 
 using namespace tcde;
+
+extern "C" int tcde_set_solve_variant(int variant) {
+    TCDE_CHECK_ARG(variant >= 0 && variant <= 2, "variant=%d (0 auto, 1 cuda-core, 2 tensor-core)", variant);
+    g_solve_variant = variant;
+    return TCDE_OK;
+}
 
 extern "C" int tcde_vector_field_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
                                         const void* bias, const void* z, void* out, int64_t n_paths, int64_t channels,
@@ -511,6 +531,15 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
     const int n_stages = (method == TCDE_RK4_38) ? 4 : (method == TCDE_MIDPOINT) ? 2 : 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == TCDE_F32) {
+        // auto: the CUDA-core kernel until the tensor-core kernel is the validated default
+        const bool want_umma = (g_solve_variant == 2);
+        if (want_umma) {
+            UmmaArgs u{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0, (float*)out,
+                       (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
+                       (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
+                       (int)n_out, (float)sign};
+            return solve_umma_f32(u, (int)hidden, (int)channels, s);
+        }
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,
                            (float*)out, (const float*)step_dt, stage_index, (const float*)stage_frac, out_step,
                            out_mode, (const float*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,

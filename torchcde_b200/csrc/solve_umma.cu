@@ -1,0 +1,431 @@
+// Hot path (ii) on the 5th-generation tensor cores: the fused fixed-step CDE solve with the
+// vector-field GEMM on tcgen05.mma (kind::tf32, 3xTF32 split) and accumulators in TMEM.
+//
+// Why tensor cores here.  At (L=256, C=8, H=32) the solve is ~700 flop/byte:
+// the CUDA-core kernel (solve_simt.cu) is bound by the FP32 FMA pipe at ~1/100 of the HBM
+// roofline.  Per Runge-Kutta stage the work is one [paths x 32] . [32 x 256] product followed by
+// a cheap contraction over channels -- GEMM-shaped, so it belongs on the tensor pipe.  fp32
+// parity (rtol 1e-4 after 1020 chaotic stages) rules out plain TF32 (10-bit mantissa); the
+// operands are therefore split  x = hi + lo  (hi = x rounded to TF32, lo = x - hi, exact) and
+//   z.W^T  ~=  z_lo.W_hi + z_hi.W_lo + z_hi.W_hi        (error ~2^-21 relative, fp32-class)
+// is accumulated in fp32 in TMEM by twelve 128x256x8 MMAs per stage.
+//
+// CTA anatomy (288 threads, one CTA per SM, all 512 TMEM columns):
+//   * two independent tiles of 128 paths; tile T owns TMEM columns [256T, 256T+256);
+//   * warps 0-3 / 4-7: the 128 "row" threads of tile 0 / 1 -- thread r owns path r of its tile:
+//     its hidden state y[32] lives in registers for all steps; per stage it reads its 256
+//     accumulators from TMEM (tcgen05.ld), adds the bias, contracts with its own dX/dt (8
+//     values from the spline row it prefetched with cp.async), does the Runge-Kutta
+//     combination in the reference's operation order, splits the next stage input into
+//     hi / lo and writes both into the K-major 128B-swizzled A tiles in shared memory;
+//   * warp 8: allocates TMEM, then only issues: wait "A ready" -> 12 x tcgen05.mma ->
+//     tcgen05.commit -> "D ready".  While tile 0's MMAs run, tile 1's rows do their epilogue
+//     and vice versa, so the tensor pipe and the FP32 pipe overlap.
+//   W^T (hi and lo, 64 KB) stays resident in shared memory for the whole solve.
+#include "common.cuh"
+
+namespace tcde {
+
+struct UmmaArgs {
+    const float* control;
+    const float* weight;
+    const float* bias;
+    const float* z0;
+    float* out;
+    const float* step_dt;
+    const int32_t* stage_index;
+    const float* stage_frac;
+    const int32_t* out_step;
+    const int32_t* out_mode;
+    const float* out_slope;
+    int64_t n_paths;
+    int64_t n_rows;
+    int control_kind, method, n_stages, n_steps, n_out;
+    float sign;
+};
+
+namespace umma {
+
+constexpr int kH = 32;            // hidden channels == K of the MMA == one 128-byte swizzled row
+constexpr int kTile = 128;        // paths per tile == UMMA M
+constexpr int kTiles = 2;         // tiles per CTA
+constexpr int kThreads = kTile * kTiles + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 columns: thread i of the warp receives columns [col, col+32) of TMEM lane (base lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: row r (M or N index) is the 128 bytes at r*128; its
+// 16-byte chunk c lives at chunk position c ^ (r & 7).  Descriptor fields (cute mma_sm100_desc.hpp):
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups,
+// version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.  Tiles are 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc(const void* tile) {
+    const uint64_t addr = (uint64_t)((smem_u32(tile) & 0x3FFFF) >> 4);
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t swz(int row, int k) {          // element offset of (row, k) in floats
+    return (uint32_t)row * 32u + (uint32_t)((((k >> 2) ^ (row & 7)) << 2) | (k & 3));
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// shared memory map (bytes)
+template <int N> struct Smem {
+    static constexpr int b_hi = 0;
+    static constexpr int b_lo = b_hi + N * 128;
+    static constexpr int a_hi = b_lo + N * 128;                         // [kTiles][128 rows][128 B]
+    static constexpr int a_lo = a_hi + kTiles * kTile * 128;
+    static constexpr int bias = a_lo + kTiles * kTile * 128;            // [N] floats
+    static constexpr int park = bias + N * 4;                           // [kTiles][2][kH][kTile] floats
+    static constexpr int raw = park + kTiles * 2 * kH * kTile * 4;      // [kTiles][6][kTile] float4
+    static constexpr int bars = raw + kTiles * 6 * kTile * 16;          // a_ready[2], d_ready[2], tmem slot
+    static constexpr int total = bars + 64;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs a) {
+    constexpr int N = kH * C;
+    static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+    static_assert(C == 8, "row prefetch and contraction below are written for 8 channels");
+    using S = Smem<N>;
+    using E = exact<float>;
+    extern __shared__ unsigned char smem_unaligned[];
+    // operand tiles of the 128-byte swizzle must start on 1024-byte boundaries of the shared window
+    unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+    float* b_hi = reinterpret_cast<float*>(smem + S::b_hi);
+    float* b_lo = reinterpret_cast<float*>(smem + S::b_lo);
+    float* bias_s = reinterpret_cast<float*>(smem + S::bias);
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
+    uint64_t* d_ready = a_ready + kTiles;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int64_t cta_path0 = (int64_t)blockIdx.x * (kTile * kTiles);
+    const int total = a.n_steps * a.n_stages;
+
+    // ---- one-time setup --------------------------------------------------------------------
+    for (int e = tid; e < N * kH; e += kThreads) {
+        const int n = e >> 5, k = e & 31;
+        const float w = a.weight[e];                     // weight[n][k], n = h*C + c
+        const float hi = tf32_hi(w);
+        b_hi[swz(n, k)] = hi;
+        b_lo[swz(n, k)] = w - hi;
+    }
+    for (int e = tid; e < N; e += kThreads) bias_s[e] = a.bias[e];
+    if (tid == 0) {
+        for (int t = 0; t < kTiles; ++t) {
+            mbar_init(&a_ready[t], kTile);
+            mbar_init(&d_ready[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kTiles * 4) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async_smem();                             // W tiles were written by the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    bool tile_live[kTiles];
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
+
+    if (warp == kTiles * 4) {
+        // ================================ MMA issuer ==========================================
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+        const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+        uint32_t phase[kTiles] = {0, 0};
+        for (int st = 0; st < total; ++st) {
+#pragma unroll
+            for (int t = 0; t < kTiles; ++t) {
+                if (!tile_live[t]) continue;
+                mbar_wait(&a_ready[t], phase[t]);
+                phase[t] ^= 1;
+                tc_fence_after();
+                if ((tid & 31) == 0) {
+                    const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
+                    const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
+                    const uint32_t d = tmem_base + (uint32_t)(t * N);
+                    // small terms first; each k-block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                    mma_commit(&d_ready[t]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================ row threads =========================================
+        const int t = warp >> 2;                          // tile of this thread
+        const int r = tid & (kTile - 1);                  // row (path) within the tile
+        const int64_t path = cta_path0 + (int64_t)t * kTile + r;
+        const bool live = path < a.n_paths;
+        const int64_t lpath = live ? path : a.n_paths - 1;
+        if (tile_live[t]) {
+            float* a_hi = reinterpret_cast<float*>(smem + S::a_hi + t * kTile * 128);
+            float* a_lo = reinterpret_cast<float*>(smem + S::a_lo + t * kTile * 128);
+            float* park = reinterpret_cast<float*>(smem + S::park) + (size_t)t * 2 * kH * kTile + r;
+            float4* raw = reinterpret_cast<float4*>(smem + S::raw) + (size_t)t * 6 * kTile + r;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N);
+            const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
+            const int row_stride = cubic ? 4 * C : C;
+            const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0);
+
+            auto fetch_row = [&](int idx) {               // (b | 2c | 3d) of interval idx -> raw[0..5]
+                const float* src = crow + (int64_t)idx * row_stride;
+                const int parts = cubic ? 6 : 2;
+                for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
+                cp_async_commit();
+            };
+            auto write_a = [&](const float* z) {          // next stage input -> swizzled hi / lo rows
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 hi, lo;
+                    hi.x = tf32_hi(z[4 * c4 + 0]); lo.x = z[4 * c4 + 0] - hi.x;
+                    hi.y = tf32_hi(z[4 * c4 + 1]); lo.y = z[4 * c4 + 1] - hi.y;
+                    hi.z = tf32_hi(z[4 * c4 + 2]); lo.z = z[4 * c4 + 2] - hi.z;
+                    hi.w = tf32_hi(z[4 * c4 + 3]); lo.w = z[4 * c4 + 3] - hi.w;
+                    const uint32_t off = (uint32_t)r * 32u + (uint32_t)((c4 ^ (r & 7)) << 2);
+                    *reinterpret_cast<float4*>(a_hi + off) = hi;
+                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[t]);
+            };
+            auto write_out = [&](int j, const float* v) {
+                if (!live) return;
+                float4* dst = reinterpret_cast<float4*>(a.out + (path * a.n_out + j) * kH);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            };
+
+            float y[kH];
+            {
+                const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 v = zp[c4];
+                    y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
+                }
+            }
+            int jn = 0;
+            while (jn < a.n_out && a.out_step[jn] < 0) { write_out(jn, y); ++jn; }
+            fetch_row(a.stage_index[0]);
+            write_a(y);
+
+            const float third = (float)(1.0 / 3.0);
+            int step = 0, sub = 0;
+            float dt = a.step_dt[0];
+            uint32_t phase = 0;
+            for (int st = 0; st < total; ++st) {
+                const bool more = st + 1 < total;
+                // dX/dt of this stage from the prefetched row (interpolation_cubic.py:331-336)
+                const float frac = a.stage_frac[st];
+                cp_async_wait<0>();
+                float dx[C];
+                {
+                    const float4 b0 = raw[0], b1 = raw[kTile];
+                    if (cubic) {
+                        const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            dx[c] = E::add(bb[c], E::mul(E::add(cc[c], E::mul(dd[c], frac)), frac));
+                    } else {
+                        dx[0] = b0.x; dx[1] = b0.y; dx[2] = b0.z; dx[3] = b0.w;
+                        dx[4] = b1.x; dx[5] = b1.y; dx[6] = b1.z; dx[7] = b1.w;
+                    }
+                }
+                if (more) fetch_row(a.stage_index[st + 1]);
+
+                mbar_wait(&d_ready[t], phase);
+                phase ^= 1;
+                tc_fence_after();
+
+                // kv[h] = sum_c (D[h*C + c] + bias[h*C + c]) * dX[c]
+                float kv[kH];
+#pragma unroll
+                for (int j = 0; j < N / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(32 * j), v);
+#pragma unroll
+                    for (int hh = 0; hh < 32 / C; ++hh) {
+                        const float4 q0 = *reinterpret_cast<const float4*>(bias_s + 32 * j + C * hh);
+                        const float4 q1 = *reinterpret_cast<const float4*>(bias_s + 32 * j + C * hh + 4);
+                        const float bq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc = fmaf(v[C * hh + c] + bq[c], dx[c], acc);
+                        kv[(32 / C) * j + hh] = (a.sign < 0.f) ? -acc : acc;
+                    }
+                }
+
+                // Runge-Kutta combination, one rounding per operation (oracle/odeint_port.py)
+                bool step_done = false;
+                float zn[kH];
+                if (a.method == TCDE_RK4_38) {
+                    if (sub == 0) {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) {
+                            park[(size_t)h * kTile] = kv[h];
+                            zn[h] = E::add(y[h], E::mul(E::mul(dt, kv[h]), third));
+                        }
+                    } else if (sub == 1) {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) {
+                            park[(size_t)(kH + h) * kTile] = kv[h];
+                            zn[h] = E::add(y[h], E::mul(dt, E::sub(kv[h], E::mul(park[(size_t)h * kTile], third))));
+                        }
+                    } else if (sub == 2) {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) {
+                            const float k2 = park[(size_t)(kH + h) * kTile];
+                            zn[h] = E::add(y[h], E::mul(dt, E::add(E::sub(park[(size_t)h * kTile], k2), kv[h])));
+                            park[(size_t)(kH + h) * kTile] = E::add(k2, kv[h]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) {
+                            const float sum = E::add(E::add(park[(size_t)h * kTile], E::mul(3.f, park[(size_t)(kH + h) * kTile])), kv[h]);
+                            zn[h] = E::add(y[h], E::mul(E::mul(sum, dt), 0.125f));
+                        }
+                        step_done = true;
+                    }
+                } else if (a.method == TCDE_MIDPOINT) {
+                    if (sub == 0) {
+                        const float half = E::mul(0.5f, dt);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) zn[h] = E::add(y[h], E::mul(kv[h], half));
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
+                        step_done = true;
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
+                    step_done = true;
+                }
+                if (step_done) {
+                    while (jn < a.n_out && a.out_step[jn] == step) {
+                        const int mode = a.out_mode[jn];
+                        if (mode == 0) write_out(jn, y);
+                        else if (mode == 1) write_out(jn, zn);
+                        else {
+                            const float slope = a.out_slope[jn];
+                            float v[kH];
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) v[h] = E::add(y[h], E::mul(slope, E::sub(zn[h], y[h])));
+                            write_out(jn, v);
+                        }
+                        ++jn;
+                    }
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) y[h] = zn[h];
+                    ++step;
+                    sub = 0;
+                    if (step < a.n_steps) dt = a.step_dt[step];
+                } else {
+                    ++sub;
+                }
+                if (more) write_a(zn);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTiles * 4) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace umma
+
+bool solve_umma_supported(int H, int C) { return H == umma::kH && C == 8; }
+
+int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream) {
+    TCDE_CHECK_SUPPORTED(solve_umma_supported(H, C), "tensor-core solve: built for hidden=32, channels=8 (got %d, %d)", H, C);
+    TCDE_CHECK_SUPPORTED((reinterpret_cast<uintptr_t>(a.control) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.z0) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+                         "tensor-core solve: control, z0 and out must be 16-byte aligned");
+    auto kern = umma::cdeint_umma_kernel<8>;
+    constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t per_cta = umma::kTile * umma::kTiles;
+    const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
+    TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
+    kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+}  // namespace tcde
