@@ -242,6 +242,8 @@ def run_gpu_arm(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     _lib.load()
+    if args.variant is not None:
+        _lib.call("tcde_set_solve_variant", args.variant)
 
     note("rank {} of {}: generating synthetic data".format(rank, world))
     x, z0, func = synthetic(BATCH, device, seed=1000 + rank)
@@ -348,6 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", type=int, default=None, help="solve kernel: 1 = CUDA-core, 2 = tcgen05 (default: library's choice)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -1,0 +1,137 @@
+"""GPU: dopri5 (this package's own adaptive driver) and the adjoint backward pass.
+
+An adaptive solver's output is defined only up to its tolerances, so these tests compare with
+tight fixed-step fp64 oracle solutions and with autograd through the fixed-step loop."""
+import math
+
+import pytest
+import torch
+
+import torchcde_b200 as cde
+from oracle import cde_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _problem(batch, length, channels, hidden, seed, dtype=torch.float32):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, length, channels, generator=gen, dtype=torch.float64).cumsum(1) / math.sqrt(length)
+    z0 = torch.randn(batch, hidden, generator=gen, dtype=torch.float64)
+    torch.manual_seed(seed)
+    func = cde.LinearVectorField(hidden, channels, dtype=dtype)
+    return x.to(dtype), z0.to(dtype), func
+
+
+def test_readme_example_default_call_runs_dopri5_with_adjoint():
+    """BASELINE config 1: the README call verbatim (README.md:29-55): default method and adjoint."""
+    batch, length, input_channels, hidden_channels = 1, 10, 2, 3
+    torch.manual_seed(0)
+    t = torch.linspace(0, 1, length)
+    x = torch.cat([t.view(1, length, 1), torch.rand(batch, length, input_channels - 1)], dim=2).to(DEV)
+
+    class F(torch.nn.Module):
+        def __init__(self):
+            super(F, self).__init__()
+            self.linear = torch.nn.Linear(hidden_channels, hidden_channels * input_channels)
+
+        def forward(self, t, z):
+            return self.linear(z).view(batch, hidden_channels, input_channels)
+
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
+    X = cde.CubicSpline(coeffs)
+    func = F().to(DEV)
+    z0 = torch.rand(batch, hidden_channels, device=DEV)
+    out = cde.cdeint(X=X, func=func, z0=z0, t=X.interval)
+    assert out.shape == (batch, 2, hidden_channels) and out.requires_grad
+    out[:, -1].sum().backward()
+    assert func.linear.weight.grad is not None and bool(torch.isfinite(func.linear.weight.grad).all())
+    want = O.cdeint_linear(coeffs.cpu().double(), O.knot_times(length, torch.float64),
+                           func.linear.weight.detach().cpu().double(), func.linear.bias.detach().cpu().double(),
+                           z0.cpu().double(), torch.tensor([0.0, 9.0], dtype=torch.float64), "rk4", 1 / 32)
+    assert torch.allclose(out.detach().cpu().double(), want, rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+def test_dopri5_matches_fine_fixed_step_solution(kind):
+    x, z0, func = _problem(64, 24, 8, 32, seed=4)
+    func = func.to(DEV)
+    with torch.no_grad():
+        if kind == "cubic":
+            control = O.hermite_backward_difference_coeffs(x)
+            X = cde.CubicSpline(control.to(DEV))
+            options = {}
+        else:
+            control = x
+            X = cde.LinearInterpolation(control.to(DEV))
+            options = {"options": dict(jump_t=X.grid_points)} if False else {}
+        t = torch.tensor([0.0, 7.5, 23.0])
+        out = cde.cdeint(X, func, z0.to(DEV), t, adjoint=False, rtol=1e-6, atol=1e-8, **options)
+        want = O.cdeint_linear(control.double(), O.knot_times(24, torch.float64),
+                               func.linear.weight.detach().cpu().double(), func.linear.bias.detach().cpu().double(),
+                               z0.double(), t.double(), "rk4", 1 / 16, kind)
+    scale = float(want.abs().max())
+    assert float((out.cpu().double() - want).abs().max()) < 2e-4 * scale
+
+
+def test_generic_func_shapes_like_reference_test_cdeint():
+    """test_cdeint.py:6-46: sigmoid field, float64 output times with a float32 state, 0-2 batch dims."""
+    gen = torch.Generator().manual_seed(11)
+    for method, kw in (("rk4", {"options": {"step_size": 1.0}}), ("dopri5", {})):
+        for batch_dims in ((), (2,), (2, 1)):
+            values = torch.rand(*batch_dims, 17, 2, generator=gen).to(DEV)
+            with torch.no_grad():
+                X = cde.CubicSpline(cde.natural_cubic_coeffs(values))
+            variable = torch.rand(*[1 for _ in batch_dims], 1, 2, generator=gen).to(DEV)
+
+            def f(t, z):
+                return z.sigmoid().unsqueeze(-1) + variable
+
+            z0 = torch.rand(*batch_dims, 4, generator=gen).to(DEV)
+            start, end = X.interval
+            out_times = torch.rand(5, dtype=torch.float64, generator=gen).sort().values.to(DEV) * (end - start) + start
+            with torch.no_grad():
+                out = cde.cdeint(X, f, z0, out_times, method=method, rtol=1e-1, atol=1e-1, adjoint=False, **kw)
+            assert out.shape == (*batch_dims, 5, 4)
+
+
+def test_prod_interface_and_gradient():
+    """test_cdeint.py:86-99: func.prod(t, z, dXdt) with the analytic solution z0 exp(-(X(T)-X(0)))."""
+    x = torch.rand(2, 5, 1, device=DEV, dtype=torch.float64)
+    with torch.no_grad():
+        X = cde.CubicSpline(cde.natural_cubic_coeffs(x))
+
+    class F:
+        def prod(self, t, z, dXdt):
+            assert t.shape == () and z.shape == (2, 3) and dXdt.shape == (2, 1)
+            return -z * dXdt
+
+    z0 = torch.rand(2, 3, device=DEV, dtype=torch.float64, requires_grad=True)
+    out = cde.cdeint(X=X, func=F(), z0=z0, t=X.interval, adjoint_params=(), rtol=1e-8, atol=1e-10)
+    exact = z0.detach() * torch.exp(-(x[:, -1] - x[:, 0]))
+    assert torch.allclose(out[:, -1].detach(), exact, rtol=1e-5, atol=1e-7)
+    out.sum().backward()
+    assert torch.allclose(z0.grad, 1 + torch.exp(-(x[:, -1] - x[:, 0])).expand_as(z0), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("method,kw", [("rk4", {"options": {"step_size": 0.25}}), ("dopri5", {})])
+def test_adjoint_gradients_match_backprop_through_the_solver(method, kw):
+    """adjoint=True (continuous adjoint, fused forward) vs adjoint=False (autograd through the stage
+    loop): same gradients up to discretisation error (test_tricks.py checks existence only)."""
+    x, z0, func = _problem(5, 9, 3, 4, seed=8, dtype=torch.float64)
+    func = func.to(DEV)
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x.to(DEV))
+    X = cde.CubicSpline(coeffs)
+    t = torch.tensor([0.0, 3.3, 8.0], dtype=torch.float64)
+    grads = []
+    for adjoint in (True, False):
+        zz = z0.to(DEV).clone().requires_grad_(True)
+        func.zero_grad()
+        out = cde.cdeint(X, func, zz, t, adjoint=adjoint, method=method, rtol=1e-9, atol=1e-11, **kw)
+        (out[:, 1].pow(2).sum() + out[:, 2].sum()).backward()
+        grads.append((zz.grad.clone(), func.linear.weight.grad.clone(), func.linear.bias.grad.clone()))
+    tol = 5e-3 if method == "rk4" else 1e-5
+    for a, b in zip(*grads):
+        assert torch.allclose(a, b, rtol=tol, atol=tol * float(b.abs().max()))

@@ -61,6 +61,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError here means header and library disagree
         fn.argtypes = argtypes
         fn.restype = restype
+    variant = os.environ.get("TCDE_SOLVE_VARIANT")
+    if variant:
+        lib.tcde_set_solve_variant(int(variant))
     _lib = lib
     return lib
 

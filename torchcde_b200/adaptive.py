@@ -1,0 +1,255 @@
+"""Adaptive (dopri5) stepping and the adjoint backward pass -- this package's own drivers.
+
+Where the reference calls ``torchdiffeq.odeint`` / ``odeint_adjoint`` with the default method
+(solver.py:226-227; ``example/time_series_classification.py:83-86`` uses dopri5 + adjoint), we
+run the drivers below instead.  They restate the *published* algorithms of torchdiffeq 0.2.x
+(``_impl/rk_common.py`` ``RKAdaptiveStepsizeODESolver`` with the Dormand-Prince tableau,
+``_impl/adjoint.py``) -- the package itself is not installable here, so, like the fixed-step
+port, the stepping is "parity unpinned" against a torchdiffeq binary; an adaptive solver's
+output is only defined up to its tolerances anyway, and that is what the tests check
+(against tight-tolerance fp64 solutions).
+
+Design for the GPU: time, step size and the controller live on the HOST as Python floats
+(double precision, the dtype torchdiffeq uses for them); the state, the seven stage slopes and
+the error estimate live on the device; each attempted step costs exactly one device->host
+read (the error ratio), which is also what torchdiffeq pays (``if accept_step``).  The error
+norm is the RMS over the *whole* state tensor, so a batch shares one step sequence
+(SURVEY.md 8e caveat 1).  The vector field is a callable ``field(t_float, y) -> dy``; for the
+linear vector field it is one fused kernel launch (``tcde_vector_field_linear``).
+"""
+import bisect
+
+import torch
+
+# Dormand-Prince 5(4), FSAL.  alpha, beta (rows), solution weights, error weights, midpoint weights
+_ALPHA = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+_BETA = (
+    (1 / 5,),
+    (3 / 40, 9 / 40),
+    (44 / 45, -56 / 15, 32 / 9),
+    (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+    (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656),
+    (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84),
+)
+_C_ERROR = (
+    35 / 384 - 1951 / 21600, 0.0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+    -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0,
+)
+_C_MID = (
+    6025192743 / 30085553152 / 2, 0.0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+    187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2,
+)
+_ORDER = 5
+
+
+def _rms(x):
+    return float(x.pow(2).mean().sqrt())
+
+
+def _combine(base, ks, weights, dt):
+    """base + sum_j (weights[j] * dt) * ks[j], skipping zero weights."""
+    out = base
+    for k, w in zip(ks, weights):
+        if w != 0.0:
+            out = out + k * (w * dt)
+    return out
+
+
+def _initial_step(field, t0, y0, f0, rtol, atol):
+    """Hairer's starting step (torchdiffeq ``_select_initial_step`` with order - 1 = 4)."""
+    scale = atol + y0.abs() * rtol
+    d0 = _rms(y0 / scale)
+    d1 = _rms(f0 / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = field(t0 + h0, y0 + h0 * f0)
+    d2 = _rms((f1 - f0) / scale) / h0
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = max(1e-6, h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / _ORDER)
+    return min(100 * h0, h1)
+
+
+def _next_step(dt, ratio, safety=0.9, ifactor=10.0, dfactor=0.2):
+    if ratio == 0:
+        return dt * ifactor
+    if ratio < 1:
+        dfactor = 1.0
+    return dt * min(ifactor, max(safety / ratio ** (1.0 / _ORDER), dfactor))
+
+
+class Dopri5:
+    """One adaptive solve of dy/dt = field(t, y) over increasing output times ``t`` (floats)."""
+
+    def __init__(self, field, y0, rtol, atol, first_step=None, max_num_steps=2 ** 31 - 1, norm=None):
+        self.field, self.rtol, self.atol = field, float(rtol), float(atol)
+        self.max_num_steps = max_num_steps
+        self.norm = norm or _rms
+        self.first_step = first_step
+        self.y0 = y0
+        self.n_accepted = 0
+        self.n_rejected = 0
+
+    def _attempt(self, t0, dt, y0, f0):
+        ks = [f0]
+        y1 = y0
+        for alpha, beta in zip(_ALPHA, _BETA):
+            ti = t0 + dt if alpha == 1.0 else t0 + alpha * dt
+            y1 = _combine(y0, ks, beta, dt)
+            ks.append(self.field(ti, y1))
+        # the last beta row equals the solution weights (FSAL): y1 is the 5th-order solution
+        err = _combine(torch.zeros_like(y0), ks, _C_ERROR, dt)
+        tol = self.atol + self.rtol * torch.max(y0.abs(), y1.abs())
+        return y1, ks, self.norm(err / tol)
+
+    def integrate(self, times):
+        out = [self.y0]
+        t0 = times[0]
+        y0 = self.y0
+        f0 = self.field(t0, y0)
+        dt = self.first_step if self.first_step is not None else _initial_step(self.field, t0, y0, f0, self.rtol,
+                                                                               self.atol)
+        t_lo, t_hi = t0, t0
+        coeff = None
+        for target in times[1:]:
+            tries = 0
+            while target > t_hi:
+                if tries >= self.max_num_steps:
+                    raise RuntimeError("max_num_steps exceeded ({}>={})".format(tries, self.max_num_steps))
+                y1, ks, ratio = self._attempt(t_hi, dt, y0, f0)
+                if ratio <= 1:
+                    y_mid = _combine(y0, ks, _C_MID, dt)
+                    coeff = self._fit(y0, y1, y_mid, ks[0], ks[-1], dt)
+                    t_lo, t_hi = t_hi, t_hi + dt
+                    y0, f0 = y1, ks[-1]
+                    self.n_accepted += 1
+                else:
+                    self.n_rejected += 1
+                dt = _next_step(dt, ratio)
+                tries += 1
+            out.append(self._evaluate(coeff, t_lo, t_hi, target))
+        return torch.stack(out, dim=0)
+
+    @staticmethod
+    def _fit(y0, y1, y_mid, f0, f1, dt):
+        a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+        b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+        c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+        return (y0, dt * f0, c, b, a)
+
+    @staticmethod
+    def _evaluate(coeff, t_lo, t_hi, t):
+        x = (t - t_lo) / (t_hi - t_lo)
+        total = coeff[0] + x * coeff[1]
+        power = x
+        for cf in coeff[2:]:
+            power = power * x
+            total = total + power * cf
+        return total
+
+
+def odeint_dopri5(field, y0, times, rtol, atol, options=None):
+    """``times``: increasing Python floats.  Returns (len(times), *y0.shape)."""
+    options = dict(options or {})
+    solver = Dopri5(field, y0, rtol, atol, first_step=options.pop("first_step", None),
+                    max_num_steps=options.pop("max_num_steps", 2 ** 31 - 1))
+    if options:
+        raise NotImplementedError("dopri5: unsupported options {}".format(sorted(options)))
+    out = solver.integrate(list(times))
+    return out, solver
+
+
+# ------------------------------------------------------------------------- fixed grids (generic)
+def odeint_fixed(field, y0, times, method, step_size):
+    """Fixed-grid euler / midpoint / rk4 (3/8 rule) on float times -- used by the adjoint pass."""
+    t0, t_end = times[0], times[-1]
+    if step_size is None:
+        grid = list(times)
+    else:
+        import math
+        n = int(math.ceil((t_end - t0) / step_size + 1))
+        grid = [t0 + i * step_size for i in range(n)]
+        grid[-1] = t_end
+    out = [y0]
+    y = y0
+    j = 1
+    for a, b in zip(grid[:-1], grid[1:]):
+        dt = b - a
+        if method == "rk4":
+            k1 = field(a, y)
+            k2 = field(a + dt / 3, y + dt * k1 / 3)
+            k3 = field(a + dt * 2 / 3, y + dt * (k2 - k1 / 3))
+            k4 = field(b, y + dt * (k1 - k2 + k3))
+            y1 = y + (k1 + 3 * (k2 + k3) + k4) * (dt * 0.125)
+        elif method == "midpoint":
+            y1 = y + dt * field(a + dt / 2, y + field(a, y) * (dt / 2))
+        else:
+            y1 = y + dt * field(a, y)
+        while j < len(times) and b >= times[j]:
+            if times[j] == b:
+                out.append(y1)
+            else:
+                out.append(y + ((times[j] - a) / (b - a)) * (y1 - y))
+            j += 1
+        y = y1
+    return torch.stack(out, dim=0)
+
+
+# ------------------------------------------------------------------------------------- adjoint
+class _Adjoint(torch.autograd.Function):
+    """Continuous adjoint (torchdiffeq ``odeint_adjoint``): the forward pass keeps only the outputs;
+    the backward pass integrates ``(y, a_y, a_params)`` backwards between consecutive output times
+    with the same solver family, evaluating the vector field under autograd for its VJPs."""
+
+    @staticmethod
+    def forward(ctx, forward_solve, vf, times, solve_aug, n_params, y0, *params):
+        ctx.vf, ctx.times, ctx.solve_aug = vf, times, solve_aug
+        with torch.no_grad():
+            ys = forward_solve(y0)
+        ctx.save_for_backward(ys, *params)
+        return ys
+
+    @staticmethod
+    def backward(ctx, grad_ys):
+        ys, *params = ctx.saved_tensors
+        vf, times = ctx.vf, ctx.times
+        params = tuple(params)
+        shapes = [ys[0].shape, ys[0].shape] + [p.shape for p in params]
+        sizes = [s.numel() for s in shapes]
+
+        def pack(parts):
+            return torch.cat([p.reshape(-1) for p in parts])
+
+        def unpack(flat):
+            outs, off = [], 0
+            for shape, n in zip(shapes, sizes):
+                outs.append(flat[off:off + n].view(shape))
+                off += n
+            return outs
+
+        def aug_field(t, flat):
+            y, a_y, *_ = unpack(flat)
+            with torch.enable_grad():
+                y_ = y.detach().requires_grad_(True)
+                f = vf(t, y_)
+                grads = torch.autograd.grad(f, (y_,) + params, -a_y, allow_unused=True)
+            vjp_y = grads[0] if grads[0] is not None else torch.zeros_like(y)
+            vjp_p = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads[1:], params)]
+            return pack([f.detach(), vjp_y] + vjp_p)
+
+        with torch.no_grad():
+            a_y = grad_ys[-1].clone()
+            a_p = [torch.zeros_like(p) for p in params]
+            for i in range(len(times) - 1, 0, -1):
+                flat0 = pack([ys[i], a_y] + a_p)
+                # integrate from times[i] back to times[i-1]: substitute s = -t
+                flat1 = ctx.solve_aug(lambda s, v: -aug_field(-s, v), flat0, [-times[i], -times[i - 1]])[-1]
+                _, a_y, *a_p = [x.clone() for x in unpack(flat1)]
+                a_y = a_y + grad_ys[i - 1]
+        return (None, None, None, None, None, a_y, *a_p)
+
+
+def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params):
+    """``forward_solve(y0) -> ys`` (time first); ``vf(t_float, y)`` differentiable in y and ``params``."""
+    params = tuple(p for p in params if p.requires_grad)
+    return _Adjoint.apply(forward_solve, vf, times, solve_aug, len(params), y0, *params)

@@ -14,9 +14,9 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, adaptive
 from .controls import CubicSpline, LinearInterpolation, _schedule_knots
-from .schedule import FIXED_METHODS, ScheduleCache, build_schedule
+from .schedule import FIXED_METHODS, ScheduleCache, build_schedule, locate
 
 _schedules = ScheduleCache()
 
@@ -252,6 +252,81 @@ def _generic_solve(X, func, z0, t, method, step_size, is_prod, known_control):
     return torch.stack(outs, dim=-2)
 
 
+# ------------------------------------------------------- fields for the host-driven drivers
+def _host_locator(X, state_dtype):
+    """``(t_float, nudge) -> (interval index, fraction)`` with exactly the casts the reference stack
+    applies to a stage time (to the state dtype by the solver, to the coefficient dtype by
+    ``_interpret_t``), evaluated on the CPU so that no device sync is needed per stage."""
+    knots = _schedule_knots(X)
+    n_rows = _control_signature(X)[3]
+
+    def where(t, nudge=0):
+        tt = torch.tensor(t, dtype=torch.float64).to(state_dtype)
+        if nudge:
+            tt = torch.nextafter(tt, tt + 1)
+        frac, index = locate(knots, tt.to(knots.dtype), n_rows)
+        return int(index), frac
+
+    return where
+
+
+def _kernel_field(X, weight, bias, z0):
+    """f(t, y) = (Linear(y).view(H, C)) @ dX/dt(t) as ONE launch of ``tcde_vector_field_linear``."""
+    kind, _, channels, n_rows = _control_signature(X)
+    hidden = z0.size(-1)
+    code = _lib.dtype_code(z0.dtype)
+    control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+    control = control.detach().reshape(-1, control.size(-2), control.size(-1)).contiguous()
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous() if bias is not None else torch.zeros(hidden * channels, dtype=z0.dtype,
+                                                                        device=z0.device)
+    where = _host_locator(X, z0.dtype)
+
+    def field(t, y, nudge=0):
+        index, frac = where(t, nudge)
+        yf = y.reshape(-1, hidden)
+        if not yf.is_contiguous():
+            yf = yf.contiguous()
+        out = torch.empty_like(yf)
+        with torch.cuda.device(y.device):
+            _lib.call("tcde_vector_field_linear", _lib.ptr(control), kind, n_rows, _lib.ptr(w), _lib.ptr(b),
+                      _lib.ptr(yf), _lib.ptr(out), yf.size(0), channels, hidden, index, float(frac), code,
+                      _lib.stream_of(yf))
+        return out.view_as(y)
+
+    return field
+
+
+def _torch_field(X, func, is_prod, known_control, z0):
+    """The reference's ``_VectorField.forward`` (solver.py:117-135) as differentiable torch ops."""
+    where = _host_locator(X, z0.dtype) if known_control else None
+
+    def field(t, y, nudge=0):
+        ts = torch.tensor(t, dtype=torch.float64).to(z0.dtype)
+        if nudge:
+            ts = torch.nextafter(ts, ts + 1)
+        ts = ts.to(y.device)
+        if known_control:
+            index, frac = where(t, nudge)
+            dx = _derivative_at(X, index, frac.to(y.device))
+        else:
+            dx = X.derivative(ts)
+        if is_prod:
+            return func.prod(ts, y, dx)
+        return (func(ts, y) @ dx.unsqueeze(-1)).squeeze(-1)
+
+    return field
+
+
+def _reverse(field):
+    return lambda s, y, nudge=0: -1.0 * field(-s, y)
+
+
+def _time_first_to_reference_layout(out):
+    dims = range(1, out.dim() - 1)
+    return out.permute(*dims, 0, -1)
+
+
 def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
     r"""Solves a system of controlled differential equations
     ``z_t = z_{t_0} + \int_{t_0}^t f(s, z_s) dX_s``  (reference: torchcde/solver.py:144-245).
@@ -290,15 +365,14 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
     if backend != "torchdiffeq":
         raise ValueError(f"Unrecognised backend={backend}")
 
-    method = kwargs.get("method", None)
+    method = kwargs.get("method", None) or "dopri5"          # torchdiffeq's default
     options = dict(kwargs.get("options", None) or {})
-    if method is None or method not in FIXED_METHODS:
+    if method not in FIXED_METHODS and method != "dopri5":
         raise NotImplementedError(
-            "torchcde_b200.cdeint: method={!r} is not built yet. This round implements torchdiffeq's fixed-step "
-            "methods {} (pass e.g. method='rk4', options={{'step_size': 1.0}}); the adaptive dopri5 default and its "
-            "adjoint are scheduled next (SURVEY.md section 7, step 7).".format(method, FIXED_METHODS))
-    step_size = options.pop("step_size", None)
-    if options:
+            "torchcde_b200.cdeint: method={!r} is not built. Available: torchdiffeq's fixed-step {} and the adaptive "
+            "'dopri5' (its default).".format(method, FIXED_METHODS))
+    step_size = options.pop("step_size", None) if method in FIXED_METHODS else None
+    if method in FIXED_METHODS and options:
         raise NotImplementedError("torchcde_b200.cdeint: unsupported solver options {}".format(sorted(options)))
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t)
@@ -322,32 +396,88 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                               "cdeint(X=X, func=func, ..., adjoint_params=adjoint_params)\n"
                               "```")
 
-    # ---- fused path: shapes are checked from metadata, nothing is evaluated on the batch ------
+    # ---- what kind of problem is this? -----------------------------------------------------------
+    field_params = None
     if sig is not None and not is_prod:
         kind, batch, channels, _ = sig
         t0 = t[0].detach().to(z0.dtype) if t.numel() else t
-        field = linear_field_of(func, z0, channels, t0)
-        if field is not None:
-            weight, bias = field
-            _shape_error_forward(batch + (channels,), tuple(z0.shape[:-1]) + (z0.size(-1), channels), z0)
-            wants_grad = torch.is_grad_enabled() and any(
-                x is not None and x.requires_grad for x in (z0, weight, bias, t, *X.buffers()))
-            if not wants_grad:
-                return _fused_solve(X, weight, bias, z0, t, method, step_size)
-
-    # ---- generic path: the reference's own compatibility check (solver.py:44-100), then our loop
-    _lib.require_cuda(z0)
-    control_gradient = X.derivative(t[0].detach())
-    if not isinstance(control_gradient, torch.Tensor):
-        raise ValueError("z0 is a tensor and so X.derivative must return a tensor as well.")
-    if is_prod:
-        vector_field = func.prod(t[0], z0, control_gradient)
-        if not isinstance(vector_field, torch.Tensor):
-            raise ValueError("z0 is a tensor and so func.prod must return a tensor as well.")
-        _shape_error_prod(tuple(control_gradient.shape), tuple(vector_field.shape), z0)
+        field_params = linear_field_of(func, z0, channels, t0)
+    if field_params is not None:
+        # shapes are checked from metadata: nothing is evaluated on the batch
+        _shape_error_forward(batch + (channels,), tuple(z0.shape[:-1]) + (z0.size(-1), channels), z0)
     else:
-        system = func(t[0], z0)
-        if not isinstance(system, torch.Tensor):
-            raise ValueError("z0 is a tensor and so func must return a tensor as well.")
-        _shape_error_forward(tuple(control_gradient.shape), tuple(system.shape), z0)
-    return _generic_solve(X, func, z0, t, method, step_size, is_prod, sig is not None)
+        # the reference's own compatibility check (solver.py:44-100): one evaluation at t[0]
+        _lib.require_cuda(z0)
+        control_gradient = X.derivative(t[0].detach())
+        if not isinstance(control_gradient, torch.Tensor):
+            raise ValueError("z0 is a tensor and so X.derivative must return a tensor as well.")
+        if is_prod:
+            vector_field = func.prod(t[0], z0, control_gradient)
+            if not isinstance(vector_field, torch.Tensor):
+                raise ValueError("z0 is a tensor and so func.prod must return a tensor as well.")
+            _shape_error_prod(tuple(control_gradient.shape), tuple(vector_field.shape), z0)
+        else:
+            system = func(t[0], z0)
+            if not isinstance(system, torch.Tensor):
+                raise ValueError("z0 is a tensor and so func must return a tensor as well.")
+            _shape_error_forward(tuple(control_gradient.shape), tuple(system.shape), z0)
+    _lib.require_cuda(z0)
+
+    if 'adjoint_params' in kwargs:
+        adjoint_params = tuple(kwargs['adjoint_params'])
+    else:
+        adjoint_params = tuple(func.parameters()) if isinstance(func, torch.nn.Module) else ()
+    differentiable = (z0, t) + tuple(X.buffers()) + (tuple(func.parameters()) if isinstance(func, torch.nn.Module)
+                                                     else ()) + adjoint_params
+    wants_grad = torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad
+                                                 for x in differentiable)
+
+    times = [float(v) for v in t.detach().cpu().tolist()]
+    flipped = len(times) > 1 and times[0] > times[1]
+    if flipped:
+        times = [-v for v in times]
+    if any(b <= a for a, b in zip(times[:-1], times[1:])):
+        raise ValueError("t must be strictly increasing or decreasing")
+
+    def fast_field():
+        f = _kernel_field(X, field_params[0], field_params[1], z0) if field_params is not None \
+            else _torch_field(X, func, is_prod, sig is not None, z0)
+        return _reverse(f) if flipped else f
+
+    def autograd_field():
+        f = _torch_field(X, func, is_prod, sig is not None, z0)
+        return _reverse(f) if flipped else f
+
+    rtol, atol = kwargs['rtol'], kwargs['atol']
+
+    def forward_values(y0):
+        """Outputs only, time first, by the fastest route."""
+        if method in FIXED_METHODS:
+            if field_params is not None:
+                out = _fused_solve(X, field_params[0], field_params[1], y0, t, method, step_size)
+                return out.movedim(-2, 0)
+            return _generic_solve(X, func, y0, t, method, step_size, is_prod, sig is not None).movedim(-2, 0)
+        return adaptive.odeint_dopri5(fast_field(), y0, times, rtol, atol, options)[0]
+
+    if not wants_grad:
+        with torch.no_grad():
+            return _time_first_to_reference_layout(forward_values(z0))
+
+    if adjoint:
+        a_rtol, a_atol = kwargs["adjoint_rtol"], kwargs["adjoint_atol"]
+        a_method = kwargs.get("adjoint_method", None) or method
+        a_options = dict(kwargs.get("adjoint_options", None) or ({"step_size": step_size} if step_size else {}))
+
+        def solve_aug(f, v, ts):
+            if a_method in FIXED_METHODS:
+                return adaptive.odeint_fixed(f, v, ts, a_method, a_options.get("step_size", None))
+            return adaptive.odeint_dopri5(f, v, ts, a_rtol, a_atol)[0]
+
+        ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params)
+        return _time_first_to_reference_layout(ys)
+
+    # adjoint=False: backpropagate through the solver's own operations, like torchdiffeq.odeint
+    if method in FIXED_METHODS:
+        return _generic_solve(X, func, z0, t, method, step_size, is_prod, sig is not None)
+    ys = adaptive.odeint_dopri5(autograd_field(), z0, times, rtol, atol, options)[0]
+    return _time_first_to_reference_layout(ys)
