@@ -151,8 +151,9 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              double sign, int dtype, void* stream);
 
 /* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic choice,
- * 1 = CUDA-core kernel (any shape), 2 = tcgen05 tensor-core kernel (hidden = 32, channels = 8;
- * TCDE_ERR_UNSUPPORTED otherwise).  Process-wide; meant for tests and benchmarks. */
+ * 1 = CUDA-core kernel (any shape), 2 / 3 = tcgen05 tensor-core kernel, one / two row threads per
+ * path (hidden = 32, channels = 8; TCDE_ERR_UNSUPPORTED otherwise).  Process-wide; meant for tests
+ * and benchmarks. */
 TCDE_API int tcde_set_solve_variant(int variant);
 
 #ifdef __cplusplus

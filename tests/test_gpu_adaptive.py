@@ -50,29 +50,55 @@ def test_readme_example_default_call_runs_dopri5_with_adjoint():
     want = O.cdeint_linear(coeffs.cpu().double(), O.knot_times(length, torch.float64),
                            func.linear.weight.detach().cpu().double(), func.linear.bias.detach().cpu().double(),
                            z0.cpu().double(), torch.tensor([0.0, 9.0], dtype=torch.float64), "rk4", 1 / 32)
-    assert torch.allclose(out.detach().cpu().double(), want, rtol=2e-3, atol=2e-4)
+    err = float((out.detach().cpu().double() - want).abs().max())
+    assert err < 5e-3 * max(1.0, float(want.abs().max())), err
 
 
-@pytest.mark.parametrize("kind", ["cubic", "linear"])
-def test_dopri5_matches_fine_fixed_step_solution(kind):
+def _exact_piecewise_linear(x, weight, bias, z0, t_end_index):
+    """For a piecewise-LINEAR control dX/dt is constant on every interval, so the linear CDE is an
+    affine constant-coefficient ODE there: one matrix exponential per interval gives the exact
+    solution (fp64) -- an oracle that involves no time stepping at all."""
+    batch, length, channels = x.shape
+    hidden = z0.size(-1)
+    w = weight.view(hidden, channels, hidden)
+    b = bias.view(hidden, channels)
+    z = torch.cat([z0, torch.ones(batch, 1, dtype=z0.dtype)], dim=1)
+    outs = {0: z0.clone()}
+    for i in range(length - 1):
+        dx = x[:, i + 1] - x[:, i]                                   # unit knots: slope == increment
+        m = torch.zeros(batch, hidden + 1, hidden + 1, dtype=z0.dtype)
+        m[:, :hidden, :hidden] = torch.einsum("hck,bc->bhk", w, dx)
+        m[:, :hidden, hidden] = torch.einsum("hc,bc->bh", b, dx)
+        z = torch.einsum("bij,bj->bi", torch.linalg.matrix_exp(m), z)
+        outs[i + 1] = z[:, :hidden].clone()
+    return outs[t_end_index]
+
+
+def test_dopri5_cubic_control_matches_fine_fixed_step_solution():
     x, z0, func = _problem(64, 24, 8, 32, seed=4)
     func = func.to(DEV)
     with torch.no_grad():
-        if kind == "cubic":
-            control = O.hermite_backward_difference_coeffs(x)
-            X = cde.CubicSpline(control.to(DEV))
-            options = {}
-        else:
-            control = x
-            X = cde.LinearInterpolation(control.to(DEV))
-            options = {"options": dict(jump_t=X.grid_points)} if False else {}
+        control = O.hermite_backward_difference_coeffs(x)
+        X = cde.CubicSpline(control.to(DEV))
         t = torch.tensor([0.0, 7.5, 23.0])
-        out = cde.cdeint(X, func, z0.to(DEV), t, adjoint=False, rtol=1e-6, atol=1e-8, **options)
+        out = cde.cdeint(X, func, z0.to(DEV), t, adjoint=False, rtol=1e-6, atol=1e-8)
         want = O.cdeint_linear(control.double(), O.knot_times(24, torch.float64),
                                func.linear.weight.detach().cpu().double(), func.linear.bias.detach().cpu().double(),
-                               z0.double(), t.double(), "rk4", 1 / 16, kind)
+                               z0.double(), t.double(), "rk4", 1 / 16, "cubic")
     scale = float(want.abs().max())
     assert float((out.cpu().double() - want).abs().max()) < 2e-4 * scale
+
+
+def test_dopri5_linear_control_matches_exact_matrix_exponential():
+    x, z0, func = _problem(48, 12, 8, 32, seed=5)
+    func = func.to(DEV)
+    with torch.no_grad():
+        X = cde.LinearInterpolation(x.to(DEV))
+        out = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8)
+        want = _exact_piecewise_linear(x.double(), func.linear.weight.detach().cpu().double(),
+                                       func.linear.bias.detach().cpu().double(), z0.double(), 11)
+    scale = float(want.abs().max())
+    assert float((out[:, -1].cpu().double() - want).abs().max()) < 5e-4 * scale
 
 
 def test_generic_func_shapes_like_reference_test_cdeint():
@@ -115,7 +141,7 @@ def test_prod_interface_and_gradient():
     assert torch.allclose(z0.grad, 1 + torch.exp(-(x[:, -1] - x[:, 0])).expand_as(z0), rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("method,kw", [("rk4", {"options": {"step_size": 0.25}}), ("dopri5", {})])
+@pytest.mark.parametrize("method,kw", [("rk4", {"options": {"step_size": 0.03125}}), ("dopri5", {})])
 def test_adjoint_gradients_match_backprop_through_the_solver(method, kw):
     """adjoint=True (continuous adjoint, fused forward) vs adjoint=False (autograd through the stage
     loop): same gradients up to discretisation error (test_tricks.py checks existence only)."""
@@ -132,6 +158,6 @@ def test_adjoint_gradients_match_backprop_through_the_solver(method, kw):
         out = cde.cdeint(X, func, zz, t, adjoint=adjoint, method=method, rtol=1e-9, atol=1e-11, **kw)
         (out[:, 1].pow(2).sum() + out[:, 2].sum()).backward()
         grads.append((zz.grad.clone(), func.linear.weight.grad.clone(), func.linear.bias.grad.clone()))
-    tol = 5e-3 if method == "rk4" else 1e-5
+    tol = 2e-3 if method == "rk4" else 1e-5
     for a, b in zip(*grads):
         assert torch.allclose(a, b, rtol=tol, atol=tol * float(b.abs().max()))

@@ -133,7 +133,8 @@ def test_vector_field_kernel_against_reference_field():
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("batch,length,channels,hidden", [(200, 64, 8, 32), (37, 20, 3, 5), (1, 10, 2, 3),
-                                                          (64, 30, 4, 64), (9, 12, 12, 16), (130, 40, 1, 7)])
+                                                          (64, 30, 4, 64), (9, 12, 12, 16), (130, 40, 1, 7),
+                                                          (77, 25, 8, 16), (50, 18, 16, 24)])
 def test_fused_solve_against_fp64_oracle(dtype, batch, length, channels, hidden):
     gen = torch.Generator().manual_seed(batch * 7 + hidden)
     x = torch.randn(batch, length, channels, generator=gen, dtype=torch.float64).cumsum(1) / math.sqrt(length)
@@ -255,8 +256,9 @@ def _set_variant(v):
     _lib.call("tcde_set_solve_variant", v)
 
 
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("batch", [1, 100, 128, 129, 256, 300, 1000])
-def test_tensor_core_variant_matches_cuda_core_and_oracle(batch):
+def test_tensor_core_variant_matches_cuda_core_and_oracle(batch, variant):
     """solve_umma.cu (3xTF32 on tcgen05, accumulators in TMEM) against solve_simt.cu and the fp64
     oracle, including partial tiles (batch not a multiple of 128 / 256)."""
     length, channels, hidden = 40, 8, 32
@@ -276,7 +278,7 @@ def test_tensor_core_variant_matches_cuda_core_and_oracle(batch):
                     _set_variant(1)
                     simt = cde.cdeint(control, func, z0.to(DEV), t_out, adjoint=False, method=method,
                                       options={"step_size": step})
-                    _set_variant(2)
+                    _set_variant(variant)
                     tc = cde.cdeint(control, func, z0.to(DEV), t_out, adjoint=False, method=method,
                                     options={"step_size": step})
                     data = co.double() if kind == "cubic" else x.float().double()
@@ -291,7 +293,8 @@ def test_tensor_core_variant_matches_cuda_core_and_oracle(batch):
         _set_variant(0)
 
 
-def test_tensor_core_variant_full_size():
+@pytest.mark.parametrize("variant", [2, 3])
+def test_tensor_core_variant_full_size(variant):
     gen = torch.Generator(device=DEV).manual_seed(0)
     B, L, C, H = 65536, 256, 8, 32
     x = torch.randn(B, L, C, generator=gen, device=DEV).cumsum(1) / math.sqrt(L)
@@ -303,7 +306,7 @@ def test_tensor_core_variant_full_size():
             coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
             X = cde.CubicSpline(coeffs)
             t = torch.tensor([0.0, L - 1.0])
-            _set_variant(2)
+            _set_variant(variant)
             out = cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options={"step_size": 1.0})
             again = cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options={"step_size": 1.0})
             assert torch.equal(out, again) and bool(torch.isfinite(out).all())

@@ -408,22 +408,398 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
     if (warp == kTiles * 4) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =================================================================================================
+// Version 2: two row threads per path.
+//
+// ncu on version 1 (profiles/r01_ncu_umma_v1_summary.csv): the tensor pipe is busy only ~60% of
+// the time because one thread per path needs ~4000 cycles for its epilogue (1336 warp
+// instructions per warp-stage, mostly dependent-latency stalls with 2 warps per scheduler),
+// longer than the 1536 cycles of the other tile's MMAs.  Here every path gets TWO threads, each
+// owning 16 of the 32 hidden units (= 128 of the 256 accumulator columns): the epilogue's
+// critical path halves and each scheduler has 4 warps to interleave.  The FP32 work uses the
+// packed FFMA2/FADD2/FMUL2 forms (two IEEE fp32 operations per instruction, same rounding as
+// the scalar forms) to halve the issue slots, and next-stage schedule entries are prefetched.
+// Thread 0 of a pair computes dX/dt and publishes it in shared memory for its partner.
+namespace v2 {
+
+constexpr int kHalf = kH / 2;                       // hidden units per thread
+constexpr int kThreads2 = kTiles * kTile * 2 + 32;  // 544
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) --------------------------------
+typedef uint64_t f2;
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// Wait for this thread's outstanding tcgen05.ld.  The destination registers are passed through the
+// statement ("+r") so that the compiler cannot schedule any use of them above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+template <int N> struct Smem2 {
+    static constexpr int b_hi = 0;
+    static constexpr int b_lo = b_hi + N * 128;
+    static constexpr int a_hi = b_lo + N * 128;                          // [kTiles][128 rows][128 B]
+    static constexpr int a_lo = a_hi + kTiles * kTile * 128;
+    static constexpr int bias = a_lo + kTiles * kTile * 128;             // [N] floats
+    static constexpr int park = bias + N * 4;                            // [kTiles][kH][kTile] floats (k1)
+    static constexpr int raw = park + kTiles * kH * kTile * 4;           // [kTiles][6][kTile] float4
+    static constexpr int dxs = raw + kTiles * 6 * kTile * 16;            // [kTiles][2][kTile][8] floats
+    static constexpr int bars = dxs + kTiles * 2 * kTile * 8 * 4;
+    static constexpr int total = bars + 64;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaArgs a) {
+    constexpr int N = kH * C;
+    static_assert(C == 8 && N == 256, "written for 8 channels x 32 hidden units");
+    using S = Smem2<N>;
+    using E = exact<float>;
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+    float* b_hi = reinterpret_cast<float*>(smem + S::b_hi);
+    float* b_lo = reinterpret_cast<float*>(smem + S::b_lo);
+    float* bias_s = reinterpret_cast<float*>(smem + S::bias);
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
+    uint64_t* d_ready = a_ready + kTiles;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int64_t cta_path0 = (int64_t)blockIdx.x * (kTile * kTiles);
+    const int total = a.n_steps * a.n_stages;
+    constexpr int kMmaWarp = kTiles * 8;
+
+    for (int e = tid; e < N * kH; e += kThreads2) {
+        const int n = e >> 5, k = e & 31;
+        const float w = a.weight[e];
+        const float hi = tf32_hi(w);
+        b_hi[swz(n, k)] = hi;
+        b_lo[swz(n, k)] = w - hi;
+    }
+    for (int e = tid; e < N; e += kThreads2) bias_s[e] = a.bias[e];
+    if (tid == 0) {
+        for (int t = 0; t < kTiles; ++t) {
+            mbar_init(&a_ready[t], 2 * kTile);
+            mbar_init(&d_ready[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    bool tile_live[kTiles];
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
+
+    if (warp == kMmaWarp) {
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+        const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+        uint32_t phase[kTiles] = {0, 0};
+        for (int st = 0; st < total; ++st) {
+#pragma unroll
+            for (int t = 0; t < kTiles; ++t) {
+                if (!tile_live[t]) continue;
+                mbar_wait(&a_ready[t], phase[t]);
+                phase[t] ^= 1;
+                tc_fence_after();
+                if ((tid & 31) == 0) {
+                    const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
+                    const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
+                    const uint32_t d = tmem_base + (uint32_t)(t * N);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                    mma_commit(&d_ready[t]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int t = warp >> 3;                          // tile
+        const int hf = (warp >> 2) & 1;                   // which half of the hidden units
+        const int r = ((warp & 3) << 5) | (tid & 31);     // row (path) within the tile == TMEM lane
+        const int64_t path = cta_path0 + (int64_t)t * kTile + r;
+        const bool live = path < a.n_paths;
+        const int64_t lpath = live ? path : a.n_paths - 1;
+        if (tile_live[t]) {
+            float* a_hi = reinterpret_cast<float*>(smem + S::a_hi + t * kTile * 128);
+            float* a_lo = reinterpret_cast<float*>(smem + S::a_lo + t * kTile * 128);
+            float* park = reinterpret_cast<float*>(smem + S::park) + ((size_t)t * kH + hf * kHalf) * kTile + r;
+            float4* raw = reinterpret_cast<float4*>(smem + S::raw) + (size_t)t * 6 * kTile + r;
+            float* dxs = reinterpret_cast<float*>(smem + S::dxs) + ((size_t)t * 2 * kTile + r) * 8;   // + buf * kTile * 8
+            const float* bias_h = bias_s + hf * kHalf * C;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N + hf * kHalf * C);
+            const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
+            const int row_stride = cubic ? 4 * C : C;
+            const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0);
+
+            auto fetch_row = [&](int idx) {
+                const float* src = crow + (int64_t)idx * row_stride;
+                const int parts = cubic ? 6 : 2;
+                for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
+                cp_async_commit();
+            };
+            auto publish_dx = [&](float frac, int buf) {  // dX/dt (interpolation_cubic.py:331-336), exact ops
+                cp_async_wait<0>();
+                const float4 b0 = raw[0], b1 = raw[kTile];
+                float4 o0 = b0, o1 = b1;
+                if (cubic) {
+                    const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
+                    const f2 fr = pk(frac, frac);
+                    f2 v;
+                    v = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr)); upk(v, o0.x, o0.y);
+                    v = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr)); upk(v, o0.z, o0.w);
+                    v = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr)); upk(v, o1.x, o1.y);
+                    v = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr)); upk(v, o1.z, o1.w);
+                }
+                float4* dst = reinterpret_cast<float4*>(dxs + (size_t)buf * kTile * 8);
+                dst[0] = o0;
+                dst[1] = o1;
+            };
+            auto write_a = [&](const float* z) {          // this thread's 16 k-values of row r, hi / lo
+#pragma unroll
+                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
+                    float4 hi, lo;
+                    hi.x = tf32_hi(z[4 * c4 + 0]); lo.x = z[4 * c4 + 0] - hi.x;
+                    hi.y = tf32_hi(z[4 * c4 + 1]); lo.y = z[4 * c4 + 1] - hi.y;
+                    hi.z = tf32_hi(z[4 * c4 + 2]); lo.z = z[4 * c4 + 2] - hi.z;
+                    hi.w = tf32_hi(z[4 * c4 + 3]); lo.w = z[4 * c4 + 3] - hi.w;
+                    const int chunk = hf * (kHalf / 4) + c4;
+                    const uint32_t off = (uint32_t)r * 32u + (uint32_t)((chunk ^ (r & 7)) << 2);
+                    *reinterpret_cast<float4*>(a_hi + off) = hi;
+                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[t]);
+            };
+            auto write_out = [&](int j, const float* v) {
+                if (!live) return;
+                float4* dst = reinterpret_cast<float4*>(a.out + (path * a.n_out + j) * kH + hf * kHalf);
+#pragma unroll
+                for (int c4 = 0; c4 < kHalf / 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            };
+
+            float y[kHalf], s23[kHalf];
+            {
+                const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH + hf * kHalf);
+#pragma unroll
+                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
+                    const float4 v = zp[c4];
+                    y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int h = 0; h < kHalf; ++h) s23[h] = 0.f;
+            }
+            int jn = 0;
+            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
+            while (jn < a.n_out && next_out < 0) {
+                write_out(jn, y);
+                ++jn;
+                next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+            }
+            if (hf == 0) {
+                fetch_row(a.stage_index[0]);
+                publish_dx(a.stage_frac[0], 0);
+            }
+            write_a(y);
+
+            const float third = (float)(1.0 / 3.0);
+            int step = 0, sub = 0;
+            float dt = a.step_dt[0];
+            float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
+            int idx1 = (total > 1) ? a.stage_index[1] : 0;          // schedule entry of stage st + 1
+            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;
+            uint32_t phase = 0;
+            for (int st = 0; st < total; ++st) {
+                const bool more = st + 1 < total;
+                if (hf == 0 && more) fetch_row(idx1);
+                const float frac_n = frac1;
+                if (st + 2 < total) {                     // prefetch the entry after next: a full stage of latency hiding
+                    idx1 = a.stage_index[st + 2];
+                    frac1 = a.stage_frac[st + 2];
+                }
+
+                mbar_wait(&d_ready[t], phase);
+                phase ^= 1;
+                tc_fence_after();
+
+                f2 dx2[C / 2];
+                {
+                    const float4* dsrc = reinterpret_cast<const float4*>(dxs + (size_t)(st & 1) * kTile * 8);
+                    const float4 p0 = dsrc[0], p1 = dsrc[1];
+                    dx2[0] = pk(p0.x, p0.y); dx2[1] = pk(p0.z, p0.w); dx2[2] = pk(p1.x, p1.y); dx2[3] = pk(p1.z, p1.w);
+                }
+                // kv[h] = sum_c (D[h*C + c] + bias[h*C + c]) * dX[c]; 16 columns (2 hidden units) per TMEM load,
+                // the next load in flight while the current one is consumed
+                float kv[kHalf];
+                uint32_t va[16], vb[16];
+                tmem_ld16_issue(taddr, va);
+#pragma unroll
+                for (int j = 0; j < kHalf / 2; ++j) {
+                    uint32_t* cur = (j & 1) ? vb : va;
+                    tmem_ld_wait(cur);
+                    if (j + 1 < kHalf / 2) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float4 q0 = *reinterpret_cast<const float4*>(bias_h + 16 * j + C * hh);
+                        const float4 q1 = *reinterpret_cast<const float4*>(bias_h + 16 * j + C * hh + 4);
+                        f2 acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 0]), __uint_as_float(cur[C * hh + 1])), pk(q0.x, q0.y)), dx2[0], pk(0.f, 0.f));
+                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 2]), __uint_as_float(cur[C * hh + 3])), pk(q0.z, q0.w)), dx2[1], acc);
+                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 4]), __uint_as_float(cur[C * hh + 5])), pk(q1.x, q1.y)), dx2[2], acc);
+                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 6]), __uint_as_float(cur[C * hh + 7])), pk(q1.z, q1.w)), dx2[3], acc);
+                        float lo, hi;
+                        upk(acc, lo, hi);
+                        const float sum = lo + hi;
+                        kv[2 * j + hh] = (a.sign < 0.f) ? -sum : sum;
+                    }
+                }
+
+                // Runge-Kutta combination, one rounding per operation, two hidden units per instruction
+                bool step_done = false;
+                float zn[kHalf];
+                const f2 dt2 = pk(dt, dt);
+                if (a.method == TCDE_RK4_38) {
+                    const f2 th2 = pk(third, third);
+                    if (sub == 0) {
+#pragma unroll
+                        for (int h = 0; h < kHalf; h += 2) {
+                            park[(size_t)h * kTile] = kv[h];
+                            park[(size_t)(h + 1) * kTile] = kv[h + 1];
+                            const f2 k1 = pk(kv[h], kv[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, k1), th2)), zn[h], zn[h + 1]);
+                        }
+                    } else if (sub == 1) {
+#pragma unroll
+                        for (int h = 0; h < kHalf; h += 2) {
+                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
+                            const f2 k2 = pk(kv[h], kv[h + 1]);
+                            s23[h] = kv[h];
+                            s23[h + 1] = kv[h + 1];
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(k2, mul2(k1, th2)))), zn[h], zn[h + 1]);
+                        }
+                    } else if (sub == 2) {
+#pragma unroll
+                        for (int h = 0; h < kHalf; h += 2) {
+                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
+                            const f2 k2 = pk(s23[h], s23[h + 1]);
+                            const f2 k3 = pk(kv[h], kv[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(k1, k2), k3))), zn[h], zn[h + 1]);
+                            upk(add2(k2, k3), s23[h], s23[h + 1]);
+                        }
+                    } else {
+                        const f2 three = pk(3.f, 3.f), eighth = pk(0.125f, 0.125f);
+#pragma unroll
+                        for (int h = 0; h < kHalf; h += 2) {
+                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
+                            const f2 sum = add2(add2(k1, mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(sum, dt2), eighth)), zn[h], zn[h + 1]);
+                        }
+                        step_done = true;
+                    }
+                } else if (a.method == TCDE_MIDPOINT) {
+                    if (sub == 0) {
+                        const float half = E::mul(0.5f, dt);
+#pragma unroll
+                        for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(kv[h], half));
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
+                        step_done = true;
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
+                    step_done = true;
+                }
+                if (step_done) {
+                    while (next_out == step) {
+                        const int mode = a.out_mode[jn];
+                        if (mode == 0) write_out(jn, y);
+                        else if (mode == 1) write_out(jn, zn);
+                        else {
+                            const float slope = a.out_slope[jn];
+                            float v[kHalf];
+#pragma unroll
+                            for (int h = 0; h < kHalf; ++h) v[h] = E::add(y[h], E::mul(slope, E::sub(zn[h], y[h])));
+                            write_out(jn, v);
+                        }
+                        ++jn;
+                        next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+                    }
+#pragma unroll
+                    for (int h = 0; h < kHalf; ++h) y[h] = zn[h];
+                    ++step;
+                    sub = 0;
+                    dt = dt_next;
+                    if (step + 1 < a.n_steps) dt_next = a.step_dt[step + 1];
+                } else {
+                    ++sub;
+                }
+                if (more) {
+                    if (hf == 0) publish_dx(frac_n, (st + 1) & 1);
+                    write_a(zn);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace v2
+
 }  // namespace umma
 
 bool solve_umma_supported(int H, int C) { return H == umma::kH && C == 8; }
 
-int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream) {
+int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t stream) {
     TCDE_CHECK_SUPPORTED(solve_umma_supported(H, C), "tensor-core solve: built for hidden=32, channels=8 (got %d, %d)", H, C);
     TCDE_CHECK_SUPPORTED((reinterpret_cast<uintptr_t>(a.control) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.z0) & 15) == 0 &&
                              (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
                          "tensor-core solve: control, z0 and out must be 16-byte aligned");
-    auto kern = umma::cdeint_umma_kernel<8>;
-    constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
-    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t per_cta = umma::kTile * umma::kTiles;
     const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
     TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
-    kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
+    if (version == 1) {
+        auto kern = umma::cdeint_umma_kernel<8>;
+        constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
+        TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
+    } else {
+        auto kern = umma::v2::cdeint_umma2_kernel<8>;
+        constexpr int smem = umma::v2::Smem2<256>::total + 1024;
+        TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)ctas, umma::v2::kThreads2, smem, stream>>>(a);
+    }
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }
