@@ -91,7 +91,7 @@ TCDE_API int tcde_rectilinear_prepare(const void* x, void* out, int64_t n_paths,
                              int64_t time_index, int dtype, int32_t* flags, void* stream);
 
 /* natural cubic spline on NaN-free knots (interpolation_cubic.py:7-53 + the Thomas solve of
- * misc.py:13-67).  workspace: device scratch of 4*length elements of `dtype` (the eliminated
+ * misc.py:13-67).  workspace: device scratch of 4*length + 8 elements of `dtype` (the eliminated
  * diagonal, shared by every series, is formed once there).  fp tolerance: a few ulp (the
  * back-substitution multiplies by a reciprocal instead of dividing).  Sets
  * TCDE_FLAG_NAN_SEEN like the Hermite builder. */
@@ -149,6 +149,10 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              const int32_t* stage_index, const void* stage_frac, int64_t n_out,
                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
                              double sign, int dtype, void* stream);
+
+/* Natural-cubic / gap-fill kernel choice: 0 = the parallel kernels (windowed sweeps, warp per path)
+ * when the path fits shared memory (default), 1 = one thread per series.  For tests / benchmarks. */
+TCDE_API int tcde_set_natural_variant(int variant);
 
 /* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic choice,
  * 1 = CUDA-core kernel (any shape), 2 / 3 = tcgen05 tensor-core kernel, one / two row threads per

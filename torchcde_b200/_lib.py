@@ -38,6 +38,7 @@ SIGNATURES = {
     "tcde_cdeint_fixed_linear": ([_p, _int, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _int, _i64, _p, _p, _p, _i64,
                                   _p, _p, _p, _dbl, _int, _p], _int),
     "tcde_set_solve_variant": ([_int], _int),
+    "tcde_set_natural_variant": ([_int], _int),
 }
 
 _lib = None

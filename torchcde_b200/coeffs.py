@@ -208,7 +208,7 @@ def _natural(x, t, version, name):
         stream = _lib.stream_of(flat)
         if p == 0:
             return out.view(*batch, length - 1, 4 * channels)
-        workspace = torch.empty(4 * length, dtype=flat.dtype, device=flat.device)
+        workspace = torch.empty(4 * length + 8, dtype=flat.dtype, device=flat.device)
         try:
             _lib.call("tcde_natural_cubic_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out),
                       _lib.ptr(workspace), p, length, channels, code, _lib.ptr(flags), stream)

@@ -269,6 +269,125 @@ linear_fill_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restri
     }
 }
 
+// Warp-per-path variant of the gap fill for length <= 32 * kFillRounds.  ncu on the
+// thread-per-series kernel above: 70% of issue slots busy at 16% of HBM peak -- the data-dependent
+// bridge loops diverge within a warp.  Here a warp stages its path in shared memory
+// ([channel][position], conflict-free) and lane l owns positions l, l+32, ...; "nearest
+// observation before / after" comes from warp ballots and bit scans (no loops, no divergence),
+// every lane then applies the reference's interpolation formula once per element, and the
+// filled tile is copied out with 128-bit coalesced stores.
+constexpr int kFillRounds = 8;
+template <typename T, bool UNIT>
+__global__ void __launch_bounds__(kThreads)
+linear_fill_warp_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_paths, int L,
+                        int C, int Lp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using E = exact<T>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * C * Lp;
+    const int rounds = (L + 31) >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / 32);
+    auto time_of = [&](int i) -> T { return UNIT ? T(i) : t[i]; };
+
+    for (int64_t p = (int64_t)blockIdx.x * (kThreads / 32) + warp; p < n_paths; p += warps_total) {
+        const T* xg = x + p * (int64_t)L * C;
+        T* og = out + p * (int64_t)L * C;
+        __syncwarp();
+        const int di = 32 / C, dc = 32 - di * C;
+        {
+            int i = lane / C, c = lane - (lane / C) * C;
+            for (int e = lane; e < L * C; e += 32) {        // coalesced load, transposed to [c][i]
+                tile[c * Lp + i] = xg[e];
+                i += di;
+                c += dc;
+                if (c >= C) { c -= C; ++i; }
+            }
+        }
+        __syncwarp();
+        for (int c = 0; c < C; ++c) {
+            T* row = tile + c * Lp;
+            T v[kFillRounds];
+            uint32_t m[kFillRounds];
+#pragma unroll
+            for (int k = 0; k < kFillRounds; ++k) {
+                const int i = 32 * k + lane;
+                v[k] = (k < rounds && i < L) ? row[i] : T(0);
+                m[k] = __ballot_sync(0xffffffffu, k < rounds && i < L && !is_nan(v[k]));
+            }
+            // first / last observation of the series, and per round the nearest ones outside it
+            int first = L, last = -1;
+#pragma unroll
+            for (int k = 0; k < kFillRounds; ++k) {
+                if (m[k]) {
+                    if (first == L) first = 32 * k + __ffs(m[k]) - 1;
+                    last = 32 * k + 31 - __clz(m[k]);
+                }
+            }
+            if (first == L) {                               // nothing observed: the zero path
+#pragma unroll
+                for (int k = 0; k < kFillRounds; ++k)
+                    if (k < rounds && 32 * k + lane < L) row[32 * k + lane] = T(0);
+                continue;
+            }
+            const T v_first = row[first], v_last = row[last];
+            __syncwarp();
+            int carry_prev = -1;
+#pragma unroll
+            for (int k = 0; k < kFillRounds; ++k) {
+                const int i = 32 * k + lane;
+                const bool inside = (k < rounds) && (i < L);
+                const bool hole = inside && is_nan(v[k]);
+                // nearest observation at or before / at or after position i
+                const uint32_t below = m[k] & (0xffffffffu >> (31 - lane));
+                int prv = below ? 32 * k + 31 - __clz(below) : carry_prev;
+                const uint32_t above = m[k] >> lane;
+                int nxt = L;
+                if (above) nxt = 32 * k + lane + __ffs(above) - 1;
+                else {
+#pragma unroll
+                    for (int k2 = kFillRounds - 1; k2 >= 0; --k2)
+                        if (k2 > k && m[k2]) nxt = 32 * k2 + __ffs(m[k2]) - 1;
+                }
+                if (m[k]) carry_prev = 32 * k + 31 - __clz(m[k]);
+                if (hole) {
+                    int lo_i, hi_i;
+                    T lo_v, hi_v;
+                    if (prv < 0) {                          // before the first observation
+                        lo_i = 0; hi_i = first; lo_v = v_first; hi_v = v_first;
+                    } else if (nxt >= L) {                  // after the last observation
+                        lo_i = last; hi_i = L - 1; lo_v = v_last; hi_v = v_last;
+                    } else {
+                        lo_i = prv; hi_i = nxt; lo_v = row[prv]; hi_v = row[nxt];
+                    }
+                    T filled;
+                    if (i == lo_i) filled = lo_v;           // an imputed end point itself
+                    else if (i == hi_i) filled = hi_v;
+                    else {
+                        const T tl = time_of(lo_i);
+                        const T ratio = E::div(E::sub(time_of(i), tl), E::sub(time_of(hi_i), tl));
+                        filled = E::add(lo_v, E::mul(ratio, E::sub(hi_v, lo_v)));
+                    }
+                    v[k] = filled;
+                }
+            }
+            __syncwarp();                                   // every gather from row[] is done
+#pragma unroll
+            for (int k = 0; k < kFillRounds; ++k)
+                if (k < rounds && 32 * k + lane < L) row[32 * k + lane] = v[k];
+        }
+        __syncwarp();
+        {
+            int i = lane / C, c = lane - (lane / C) * C;
+            for (int e = lane; e < L * C; e += 32) {
+                og[e] = tile[c * Lp + i];
+                i += di;
+                c += dc;
+                if (c >= C) { c -= C; ++i; }
+            }
+        }
+    }
+}
+
 // misc.forward_fill (misc.py:103-126) and _prepare_rectilinear_interpolation
 // (interpolation_linear.py:87-128).  RECT = false: out has L rows; RECT = true: 2L-1 rows, row
 // 2i = held[i], row 2i+1 = held[i] except the time channel which takes held[i+1].
@@ -346,7 +465,169 @@ __global__ void natural_prep_kernel(const T* __restrict__ t, T* __restrict__ ws,
             mult[i] = w;
             rnd[i] = E::div(T(1), nd);
         }
+        // Window sizes for the parallel sweeps of natural_win_kernel: the forward recurrence
+        // f[i] = rhs[i] - mult[i] f[i-1] forgets f[i-w] by the factor prod |mult|, the backward one
+        // k[i] = (f[i] - rdt[i] k[i+1]) rnd[i] forgets k[i+w] by prod |rdt rnd|; both factors are
+        // ~0.27 per knot for a diagonally dominant system.  A window is long enough when that
+        // product is below eps/16 (or it reaches the end of the series, where the start is exact).
+        const T tol = (sizeof(T) == 4) ? T(3.7e-9) : T(1.4e-17);
+        int wf = 0, wb = 0;
+        if (L > 2) {
+            for (int i = 1; i < L; ++i) {
+                T prod = T(1);
+                int w = 0;
+                for (int j = i; j >= 1 && prod > tol; --j) { prod *= fabs(mult[j]); ++w; }
+                wf = max(wf, w);
+            }
+            for (int i = 0; i < L - 1; ++i) {
+                T prod = T(1);
+                int w = 0;
+                for (int j = i; j < L - 1 && prod > tol; ++j) { prod *= fabs(rdt[j] * rnd[j]); ++w; }
+                wb = max(wb, w);
+            }
+            mult[0] = T(0);
+        }
+        ws[4 * L] = T(wf);
+        ws[4 * L + 1] = T(wb);
     }
+}
+
+// Natural cubic spline, parallel version.  One path at a time per CTA; thread = (series, chunk of
+// G consecutive knots).  Each thread runs the two Thomas recurrences over its chunk preceded by
+// a warm-up window (sizes from natural_prep_kernel), so all 256 threads sweep concurrently
+// instead of one thread per series walking all L knots: the sweeps stop being the
+// latency-bound phase that ncu showed (issue slots 28% busy, DRAM 11%).  The result equals the
+// sequential recurrence up to a truncated influence below eps/16 -- the same few-ulp class as
+// replacing the division by a multiplication with 1/nd.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restrict__ out, int64_t n_paths, int L,
+                   int C, int Lp, int G, int TR, int use_bulk, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using E = exact<T>;
+    const int row_elems = 4 * C;
+    T* ot0 = reinterpret_cast<T*>(smem_raw);
+    T* ot1 = ot0 + (size_t)TR * row_elems;
+    T* rdt = ot1 + (size_t)TR * row_elems;
+    T* rdt2 = rdt + L;
+    T* mult = rdt2 + L;
+    T* rnd = mult + L;
+    T* xs = rnd + L + 8;                 // [C][Lp]
+    T* fs = xs + (size_t)C * Lp;         // forward-sweep values
+    T* ks = fs + (size_t)C * Lp;         // knot slopes
+
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 4 * L + 2; e += kThreads) rdt[e] = ws[e];
+    __syncthreads();
+    const int wf = (int)rdt[4 * L], wb = (int)rdt[4 * L + 1];
+    const int n_chunks = (L + G - 1) / G;
+    const int n_items = C * n_chunks;
+    const int di = kThreads / C, dc = kThreads - di * C;
+    bool saw_nan = false;
+    int buf = 0;
+
+    for (int64_t p = blockIdx.x; p < n_paths; p += gridDim.x) {
+        __syncthreads();                 // the previous path's coefficient phase is done with xs / ks
+        {
+            const T* xg = x + p * (int64_t)L * C;
+            int i = tid / C, c = tid - (tid / C) * C;
+            for (int e = tid; e < L * C; e += kThreads) {
+                const T v = xg[e];
+                saw_nan |= is_nan(v);
+                xs[c * Lp + i] = v;
+                i += di;
+                c += dc;
+                if (c >= C) { c -= C; ++i; }
+            }
+        }
+        __syncthreads();
+        if (L > 2) {
+            for (int it = tid; it < n_items; it += kThreads) {          // forward sweep, windowed
+                const int c = it % C, j = it / C;
+                const int g0 = j * G, g1 = min(g0 + G, L);
+                const T* xr = xs + c * Lp;
+                T* fr = fs + c * Lp;
+                T f = T(0);
+                int i = max(g0 - wf, 0);
+                T x_lo = xr[i], sc_prev = T(0);
+                if (i > 0) sc_prev = E::mul(E::mul(T(3), E::sub(x_lo, xr[i - 1])), rdt2[i - 1]);
+                for (; i < g1; ++i) {
+                    T sc = T(0);
+                    if (i < L - 1) {
+                        const T x_hi = xr[i + 1];
+                        sc = E::mul(E::mul(T(3), E::sub(x_hi, x_lo)), rdt2[i]);
+                        x_lo = x_hi;
+                    }
+                    f = E::sub(E::add(sc, sc_prev), E::mul(mult[i], f));     // cubic.py:36-39, misc.py:61
+                    sc_prev = sc;
+                    if (i >= g0) fr[i] = f;
+                }
+            }
+            __syncthreads();
+            for (int it = tid; it < n_items; it += kThreads) {          // back substitution, windowed
+                const int c = it % C, j = it / C;
+                const int g0 = j * G, g1 = min(g0 + G, L);
+                const T* fr = fs + c * Lp;
+                T* kr = ks + c * Lp;
+                T k = T(0);
+                for (int i = min(g1 - 1 + wb, L - 1); i >= g0; --i) {
+                    k = E::mul(E::sub(fr[i], E::mul(rdt[i], k)), rnd[i]);    // misc.py:63-65 (rdt[L-1] = 0)
+                    if (i < g1) kr[i] = k;
+                }
+            }
+        }
+        __syncthreads();
+        for (int r0 = 0; r0 < L - 1; r0 += TR, buf ^= 1) {
+            const int nr = min(TR, L - 1 - r0);
+            if (use_bulk && tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+            T* ot = buf ? ot1 : ot0;
+            int i = tid / C, c = tid - (tid / C) * C;
+            for (int e = tid; e < nr * C; e += kThreads) {
+                const int r = r0 + i;
+                const T* xr = xs + c * Lp + r;
+                const T* kr = ks + c * Lp + r;
+                const T xl = xr[0], xh = xr[1];
+                T b, two_c, three_d;
+                if (L == 2) {
+                    b = E::div(E::sub(xh, xl), mult[0]);
+                    two_c = T(0);
+                    three_d = T(0);
+                } else {
+                    const T kl = kr[0], kh = kr[1];
+                    const T six = E::mul(T(2), E::mul(T(3), E::sub(xh, xl)));
+                    const T sr = E::mul(six, rdt[r]);
+                    b = kl;
+                    two_c = E::mul(E::sub(E::sub(sr, E::mul(T(4), kl)), E::mul(T(2), kh)), rdt[r]);
+                    three_d = E::mul(E::add(-sr, E::mul(T(3), E::add(kl, kh))), rdt2[r]);
+                }
+                T* row = ot + (size_t)i * row_elems + c;
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq) {
+                    const int w = (kq + i) & 3;
+                    const T v = (w == 0) ? xl : (w == 1) ? b : (w == 2) ? two_c : three_d;
+                    row[w * C] = v;
+                }
+                i += di;
+                c += dc;
+                if (c >= C) { c -= C; ++i; }
+            }
+            T* gp = out + (p * (int64_t)(L - 1) + r0) * row_elems;
+            if (use_bulk) {
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_store(gp, ot, (uint32_t)((size_t)nr * row_elems * sizeof(T)));
+                    bulk_commit();
+                }
+            } else {
+                __syncthreads();
+                for (int e = tid; e < nr * row_elems; e += kThreads) gp[e] = ot[e];
+            }
+        }
+    }
+    if (use_bulk && tid == 0) bulk_wait_read<0>();
+    if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
 }
 
 // One CTA per group of S paths.  Phase 1: coalesced load, transposed into shared memory as
@@ -631,6 +912,9 @@ nan_flag_kernel(const T* __restrict__ x, int64_t n, int32_t* __restrict__ flags)
 // =========================================================================================
 // launchers
 // =========================================================================================
+static int g_fill_variant = 0;        // 0 = warp-per-path gap fill when it fits, 1 = one thread per series
+static int g_natural_variant = 0;     // 0 = windowed parallel sweeps when they fit, 1 = one thread per series
+
 static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t n_items) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
@@ -690,6 +974,21 @@ static int launch_natural(const T* x, const T* t, T* out, T* ws, int64_t n_paths
     int TR = (int)(8192 / row_bytes);
     if (TR < 1) TR = 1;
     if (TR > L - 1) TR = L - 1;
+    {
+        // parallel windowed sweeps: one path per CTA iteration, thread = (series, chunk of G knots)
+        const int Lpw = ((L + 31) / 32) * 32 + 1;
+        int G = (int)(((int64_t)L * C + kThreads - 1) / kThreads);
+        if (G < 4) G = 4;
+        const size_t smem_w = 2 * TR * row_bytes + (size_t)(4 * L + 8) * sizeof(T) + (size_t)3 * C * Lpw * sizeof(T) + 16;
+        if (smem_w <= 64 * 1024 && g_natural_variant != 1) {
+            auto kw = natural_win_kernel<T>;
+            TCDE_CHECK_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            const int grid = persistent_grid((const void*)kw, kThreads, smem_w, n_paths);
+            kw<<<grid, kThreads, smem_w, stream>>>(x, ws, out, n_paths, L, C, Lpw, G, TR, aligned16(out) ? 1 : 0, flags);
+            TCDE_CHECK_CUDA(cudaGetLastError());
+            return TCDE_OK;
+        }
+    }
     int cp = 1;
     while (cp < C && cp < 32) cp <<= 1;
     const int Lp = ((L + 31) / 32) * 32 + 32 / cp;
@@ -745,9 +1044,26 @@ extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t
     const int64_t n_series = n_paths * channels;
     if (n_series == 0) return TCDE_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int L = (int)length, C = (int)channels;
+    {
+        // warp-per-path kernel when a path fits a warp's shared-memory tile
+        const int Lp = ((L + 31) / 32) * 32 + 1;
+        const size_t elem = (dtype == TCDE_F32) ? 4 : 8;
+        const size_t smem = (size_t)(kThreads / 32) * C * Lp * elem;
+        if (L <= 32 * kFillRounds && smem <= 72 * 1024 && g_fill_variant != 1) {
+            const void* kern = (dtype == TCDE_F32)
+                ? (t ? (const void*)linear_fill_warp_kernel<float, false> : (const void*)linear_fill_warp_kernel<float, true>)
+                : (t ? (const void*)linear_fill_warp_kernel<double, false> : (const void*)linear_fill_warp_kernel<double, true>);
+            TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = persistent_grid(kern, kThreads, smem, (n_paths + kThreads / 32 - 1) / (kThreads / 32));
+            const int Li = L, Ci = C, Lpi = Lp;
+            void* args[] = {(void*)&x, (void*)&t, (void*)&out, (void*)&n_paths, (void*)&Li, (void*)&Ci, (void*)&Lpi};
+            TCDE_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, smem, s));
+            return TCDE_OK;
+        }
+    }
     const int64_t blocks = (n_series + kThreads - 1) / kThreads;
     TCDE_CHECK_SUPPORTED(blocks < (1ll << 31), "too many series");
-    const int L = (int)length, C = (int)channels;
     if (dtype == TCDE_F32) {
         if (t) linear_fill_kernel<float, false><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, (const float*)t, (float*)out, n_series, L, C);
         else linear_fill_kernel<float, true><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, nullptr, (float*)out, n_series, L, C);
@@ -844,5 +1160,12 @@ extern "C" int tcde_nan_flag(const void* x, int64_t n, int dtype, int32_t* flags
     if (dtype == TCDE_F32) nan_flag_kernel<float><<<(unsigned)blocks, kThreads, 0, s>>>((const float*)x, n, flags);
     else nan_flag_kernel<double><<<(unsigned)blocks, kThreads, 0, s>>>((const double*)x, n, flags);
     TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+extern "C" int tcde_set_natural_variant(int variant) {
+    TCDE_CHECK_ARG(variant == 0 || variant == 1, "variant=%d (0 parallel kernels, 1 one thread per series)", variant);
+    g_natural_variant = variant;
+    g_fill_variant = variant;
     return TCDE_OK;
 }

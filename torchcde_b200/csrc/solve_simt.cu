@@ -550,6 +550,7 @@ struct UmmaArgs {
     int64_t n_paths; int64_t n_rows;
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
+    int split_terms;
 };
 bool solve_umma_supported(int H, int C);
 int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t stream);
@@ -561,8 +562,9 @@ static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core scalar FFMA, 2 / 3 te
 using namespace tcde;
 
 extern "C" int tcde_set_solve_variant(int variant) {
-    TCDE_CHECK_ARG(variant >= 0 && variant <= 4,
-                   "variant=%d (0 auto, 1 cuda-core scalar FFMA, 2 tensor-core v1, 3 tensor-core v2, 4 cuda-core FFMA2)",
+    TCDE_CHECK_ARG(variant >= 0 && variant <= 6,
+                   "variant=%d (0 auto, 1 cuda-core scalar FFMA, 2 tensor-core v1, 3 tensor-core v2, 4 cuda-core FFMA2, "
+                   "5 / 6 = timing experiments: v1 / v2 with a single TF32 term, WRONG results)",
                    variant);
     g_solve_variant = variant;
     return TCDE_OK;
@@ -610,19 +612,19 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
         const bool umma_ok = solve_umma_supported((int)hidden, (int)channels) &&
                              ((reinterpret_cast<uintptr_t>(control) | reinterpret_cast<uintptr_t>(z0) |
                                reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-        const bool want_umma = (g_solve_variant == 2 || g_solve_variant == 3) || (g_solve_variant == 0 && umma_ok);
+        const bool want_umma = (g_solve_variant == 2 || g_solve_variant == 3 || g_solve_variant >= 5) || (g_solve_variant == 0 && umma_ok);
         if (want_umma) {
             UmmaArgs u{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0, (float*)out,
                        (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
-                       (int)n_out, (float)sign};
-            return solve_umma_f32(u, (int)hidden, (int)channels, g_solve_variant == 3 ? 2 : 1, s);
+                       (int)n_out, (float)sign, (g_solve_variant == 5 || g_solve_variant == 6) ? 1 : 3};
+            return solve_umma_f32(u, (int)hidden, (int)channels, (g_solve_variant == 3 || g_solve_variant == 6) ? 2 : 1, s);
         }
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,
                            (float*)out, (const float*)step_dt, stage_index, (const float*)stage_frac, out_step,
                            out_mode, (const float*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
                            control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (float)sign};
-        return solve_simt_f32(a, g_solve_variant != 1, s);
+        return solve_simt_f32(a, g_solve_variant == 4, s);   // FFMA2 path measured slower (34.6 vs 31.6 ms): opt-in only
     }
     SolveArgs<double> a{(const double*)control, (const double*)weight, (const double*)bias, (const double*)z0,
                         (double*)out, (const double*)step_dt, stage_index, (const double*)stage_frac, out_step,

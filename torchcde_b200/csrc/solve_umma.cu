@@ -42,6 +42,7 @@ struct UmmaArgs {
     int64_t n_rows;
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
+    int split_terms;     // 3 = 3xTF32 (the product); 1 = hi.hi only -- a TIMING EXPERIMENT for profiling, never dispatched by default
 };
 
 namespace umma {
@@ -211,12 +212,17 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
                     // small terms first; each k-block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
+                    if (a.split_terms == 3) {
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                    } else {
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+                    }
                     mma_commit(&d_ready[t]);
                 }
                 __syncwarp();
@@ -530,12 +536,17 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
+                    if (a.split_terms == 3) {
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                    } else {
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+                    }
                     mma_commit(&d_ready[t]);
                 }
                 __syncwarp();
