@@ -150,6 +150,10 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
                              double sign, int dtype, void* stream);
 
+/* Profiling aid: a device buffer of 64 x 8 int64 that the tensor-core solve kernel (variant 2)
+ * fills with clock64 stamps of CTA 0 / tile 0 for its first 64 stages; NULL (default) disables. */
+TCDE_API int tcde_set_trace_buffer(void* device_buffer);
+
 /* Natural-cubic / gap-fill kernel choice: 0 = the parallel kernels (windowed sweeps, warp per path)
  * when the path fits shared memory (default), 1 = one thread per series.  For tests / benchmarks. */
 TCDE_API int tcde_set_natural_variant(int variant);

@@ -39,6 +39,7 @@ SIGNATURES = {
                                   _p, _p, _p, _dbl, _int, _p], _int),
     "tcde_set_solve_variant": ([_int], _int),
     "tcde_set_natural_variant": ([_int], _int),
+    "tcde_set_trace_buffer": ([_p], _int),
 }
 
 _lib = None

@@ -551,15 +551,22 @@ struct UmmaArgs {
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
     int split_terms;
+    long long* trace;
 };
 bool solve_umma_supported(int H, int C);
 int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t stream);
 
+static long long* g_trace = nullptr;   // profiling aid: device buffer for in-kernel clock stamps (see tcde_set_trace_buffer)
 static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core scalar FFMA, 2 / 3 tensor-core v1 / v2, 4 CUDA-core FFMA2
 
 }  // namespace tcde
 
 using namespace tcde;
+
+extern "C" int tcde_set_trace_buffer(void* device_buffer) {
+    g_trace = static_cast<long long*>(device_buffer);
+    return TCDE_OK;
+}
 
 extern "C" int tcde_set_solve_variant(int variant) {
     TCDE_CHECK_ARG(variant >= 0 && variant <= 6,
@@ -617,7 +624,7 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
             UmmaArgs u{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0, (float*)out,
                        (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
-                       (int)n_out, (float)sign, (g_solve_variant == 5 || g_solve_variant == 6) ? 1 : 3};
+                       (int)n_out, (float)sign, (g_solve_variant == 5 || g_solve_variant == 6) ? 1 : 3, g_trace};
             return solve_umma_f32(u, (int)hidden, (int)channels, (g_solve_variant == 3 || g_solve_variant == 6) ? 2 : 1, s);
         }
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,

@@ -43,6 +43,7 @@ struct UmmaArgs {
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
     int split_terms;     // 3 = 3xTF32 (the product); 1 = hi.hi only -- a TIMING EXPERIMENT for profiling, never dispatched by default
+    long long* trace;    // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
 };
 
 namespace umma {
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
+                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                     // small terms first; each k-block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
                     if (a.split_terms == 3) {
 #pragma unroll
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
                     }
                     mma_commit(&d_ready[t]);
+                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             }
@@ -315,9 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 }
                 if (more) fetch_row(a.stage_index[st + 1]);
 
+                const bool tr = a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
+                if (tr) a.trace[st * 8 + 2] = clock64();
                 mbar_wait(&d_ready[t], phase);
                 phase ^= 1;
                 tc_fence_after();
+                if (tr) a.trace[st * 8 + 3] = clock64();
 
                 // kv[h] = sum_c (D[h*C + c] + bias[h*C + c]) * dX[c]
                 float kv[kH];
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     }
                 }
 
+                if (tr) a.trace[st * 8 + 4] = clock64();
                 // Runge-Kutta combination, one rounding per operation (oracle/odeint_port.py)
                 bool step_done = false;
                 float zn[kH];
@@ -405,7 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 } else {
                     ++sub;
                 }
+                if (tr) a.trace[st * 8 + 5] = clock64();
                 if (more) write_a(zn);
+                if (tr) a.trace[st * 8 + 6] = clock64();
             }
         }
     }
