@@ -425,23 +425,27 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
 
 
 // =================================================================================================
-// Version 2: two row threads per path.
+// Version 2: two row threads per path, nothing but registers on the post-MMA critical path.
 //
-// ncu on version 1 (profiles/r01_ncu_umma_v1_summary.csv): the tensor pipe is busy only ~60% of
-// the time because one thread per path needs ~4000 cycles for its epilogue (1336 warp
-// instructions per warp-stage, mostly dependent-latency stalls with 2 warps per scheduler),
-// longer than the 1536 cycles of the other tile's MMAs.  Here every path gets TWO threads, each
-// owning 16 of the 32 hidden units (= 128 of the 256 accumulator columns): the epilogue's
-// critical path halves and each scheduler has 4 warps to interleave.  The FP32 work uses the
-// packed FFMA2/FADD2/FMUL2 forms (two IEEE fp32 operations per instruction, same rounding as
-// the scalar forms) to halve the issue slots, and next-stage schedule entries are prefetched.
-// Thread 0 of a pair computes dX/dt and publishes it in shared memory for its partner.
+// In-kernel clock stamps of version 1 (scripts/trace_umma.py, profiles/r01_umma_trace.txt) show
+// that a tile's stage is a serial chain -- 12 MMAs issued+executed (~1250 cycles), completion
+// visible to the rows (~500), contraction (~1330), Runge-Kutta combination (~1130, dominated by
+// shared-memory round trips of the parked slopes), hi/lo split + store + fence + arrive (~720),
+// wake-up of the issuer (~280) -- so the tensor pipe idles half of the time and the chain, not
+// the MMA count, sets the pace.  This version shortens the chain:
+//   * every path gets TWO threads, each owning 16 of the 32 hidden units (128 accumulator columns);
+//   * k1 and k2(+k3) stay in registers (no shared-memory parking);
+//   * everything that does not depend on the MMA result runs BEFORE the wait, in the MMA's shadow:
+//     the spline row is loaded (read-only 128-bit loads), dX/dt is formed, and the bias part of
+//     the contraction  sum_c bias[h,c] dX[c]  is computed;
+//   * after the wait only  sum_c D[h,c] dX[c]  remains: packed FFMA2 on 16-column TMEM loads that
+//     are issued one ahead, then the packed Runge-Kutta combination, the TF32 split and the store.
 namespace v2 {
 
 constexpr int kHalf = kH / 2;                       // hidden units per thread
 constexpr int kThreads2 = kTiles * kTile * 2 + 32;  // 544
 
-// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) --------------------------------
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, IEEE rounding per lane) ----------
 typedef uint64_t f2;
 __device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
@@ -476,10 +480,8 @@ template <int N> struct Smem2 {
     static constexpr int a_hi = b_lo + N * 128;                          // [kTiles][128 rows][128 B]
     static constexpr int a_lo = a_hi + kTiles * kTile * 128;
     static constexpr int bias = a_lo + kTiles * kTile * 128;             // [N] floats
-    static constexpr int park = bias + N * 4;                            // [kTiles][kH][kTile] floats (k1)
-    static constexpr int raw = park + kTiles * kH * kTile * 4;           // [kTiles][6][kTile] float4
-    static constexpr int dxs = raw + kTiles * 6 * kTile * 16;            // [kTiles][2][kTile][8] floats
-    static constexpr int bars = dxs + kTiles * 2 * kTile * 8 * 4;
+    static constexpr int park = bias + N * 4;                            // [2 (y, k1)][kTiles][kH][kTile] floats
+    static constexpr int bars = park + 2 * kTiles * kH * kTile * 4;
     static constexpr int total = bars + 64;
 };
 
@@ -545,6 +547,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
+                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                     if (a.split_terms == 3) {
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
                     }
                     mma_commit(&d_ready[t]);
+                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             }
@@ -571,37 +575,32 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
         if (tile_live[t]) {
             float* a_hi = reinterpret_cast<float*>(smem + S::a_hi + t * kTile * 128);
             float* a_lo = reinterpret_cast<float*>(smem + S::a_lo + t * kTile * 128);
-            float* park = reinterpret_cast<float*>(smem + S::park) + ((size_t)t * kH + hf * kHalf) * kTile + r;
-            float4* raw = reinterpret_cast<float4*>(smem + S::raw) + (size_t)t * 6 * kTile + r;
-            float* dxs = reinterpret_cast<float*>(smem + S::dxs) + ((size_t)t * 2 * kTile + r) * 8;   // + buf * kTile * 8
             const float* bias_h = bias_s + hf * kHalf * C;
+            // y and k1 are parked in shared memory ([h][row]: conflict-free) between stages: with 544
+            // threads the register file allows 96 registers per thread, and only the Runge-Kutta
+            // phase needs them (all loads first, then the arithmetic, then the stores)
+            float* ypark = reinterpret_cast<float*>(smem + S::park) + ((size_t)t * kH + hf * kHalf) * kTile + r;
+            float* kpark = ypark + (size_t)kTiles * kH * kTile;
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N + hf * kHalf * C);
             const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
             const int row_stride = cubic ? 4 * C : C;
-            const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0);
+            const float4* crow = reinterpret_cast<const float4*>(a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0));
+            const bool negate = a.sign < 0.f;
 
-            auto fetch_row = [&](int idx) {
-                const float* src = crow + (int64_t)idx * row_stride;
-                const int parts = cubic ? 6 : 2;
-                for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
-                cp_async_commit();
-            };
-            auto publish_dx = [&](float frac, int buf) {  // dX/dt (interpolation_cubic.py:331-336), exact ops
-                cp_async_wait<0>();
-                const float4 b0 = raw[0], b1 = raw[kTile];
-                float4 o0 = b0, o1 = b1;
+            // dX/dt of interval idx at fraction frac (interpolation_cubic.py:331-336), one rounding per op
+            auto slope = [&](int idx, float frac, f2* dx2) {
+                const float4* src = crow + (size_t)idx * (row_stride / 4);
+                const float4 b0 = __ldg(src), b1 = __ldg(src + 1);
                 if (cubic) {
-                    const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
+                    const float4 c0 = __ldg(src + 2), c1 = __ldg(src + 3), d0 = __ldg(src + 4), d1 = __ldg(src + 5);
                     const f2 fr = pk(frac, frac);
-                    f2 v;
-                    v = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr)); upk(v, o0.x, o0.y);
-                    v = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr)); upk(v, o0.z, o0.w);
-                    v = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr)); upk(v, o1.x, o1.y);
-                    v = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr)); upk(v, o1.z, o1.w);
+                    dx2[0] = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr));
+                    dx2[1] = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr));
+                    dx2[2] = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr));
+                    dx2[3] = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr));
+                } else {
+                    dx2[0] = pk(b0.x, b0.y); dx2[1] = pk(b0.z, b0.w); dx2[2] = pk(b1.x, b1.y); dx2[3] = pk(b1.z, b1.w);
                 }
-                float4* dst = reinterpret_cast<float4*>(dxs + (size_t)buf * kTile * 8);
-                dst[0] = o0;
-                dst[1] = o1;
             };
             auto write_a = [&](const float* z) {          // this thread's 16 k-values of row r, hi / lo
 #pragma unroll
@@ -627,8 +626,11 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                 for (int c4 = 0; c4 < kHalf / 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
             };
 
-            float y[kHalf], s23[kHalf];
+            float s23[kHalf];
+            int jn = 0;
+            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
             {
+                float y[kHalf];
                 const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH + hf * kHalf);
 #pragma unroll
                 for (int c4 = 0; c4 < kHalf / 4; ++c4) {
@@ -636,50 +638,57 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
                 }
 #pragma unroll
-                for (int h = 0; h < kHalf; ++h) s23[h] = 0.f;
+                for (int h = 0; h < kHalf; ++h) {
+                    s23[h] = 0.f;
+                    ypark[(size_t)h * kTile] = y[h];
+                    kpark[(size_t)h * kTile] = 0.f;
+                }
+                while (jn < a.n_out && next_out < 0) {
+                    write_out(jn, y);
+                    ++jn;
+                    next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+                }
+                write_a(y);
             }
-            int jn = 0;
-            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
-            while (jn < a.n_out && next_out < 0) {
-                write_out(jn, y);
-                ++jn;
-                next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
-            }
-            if (hf == 0) {
-                fetch_row(a.stage_index[0]);
-                publish_dx(a.stage_frac[0], 0);
-            }
-            write_a(y);
 
             const float third = (float)(1.0 / 3.0);
             int step = 0, sub = 0;
             float dt = a.step_dt[0];
             float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
-            int idx1 = (total > 1) ? a.stage_index[1] : 0;          // schedule entry of stage st + 1
-            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;
+            int idx0 = a.stage_index[0];                  // schedule entry of the current stage
+            float frac0 = a.stage_frac[0];
             uint32_t phase = 0;
             for (int st = 0; st < total; ++st) {
                 const bool more = st + 1 < total;
-                if (hf == 0 && more) fetch_row(idx1);
-                const float frac_n = frac1;
-                if (st + 2 < total) {                     // prefetch the entry after next: a full stage of latency hiding
-                    idx1 = a.stage_index[st + 2];
-                    frac1 = a.stage_frac[st + 2];
+                // ---- in the shadow of this stage's MMAs: dX/dt and the bias part of the contraction ----
+                f2 dx2[C / 2];
+                slope(idx0, frac0, dx2);
+                if (more) {                               // next stage's schedule entry: a full stage of latency hiding
+                    idx0 = a.stage_index[st + 1];
+                    frac0 = a.stage_frac[st + 1];
+                }
+                float kv[kHalf];
+#pragma unroll
+                for (int h = 0; h < kHalf; ++h) {
+                    const float4 q0 = *reinterpret_cast<const float4*>(bias_h + C * h);
+                    const float4 q1 = *reinterpret_cast<const float4*>(bias_h + C * h + 4);
+                    f2 acc = mul2(pk(q0.x, q0.y), dx2[0]);
+                    acc = fma2(pk(q0.z, q0.w), dx2[1], acc);
+                    acc = fma2(pk(q1.x, q1.y), dx2[2], acc);
+                    acc = fma2(pk(q1.z, q1.w), dx2[3], acc);
+                    float lo, hi;
+                    upk(acc, lo, hi);
+                    kv[h] = lo + hi;
                 }
 
+                const bool tr = a.trace && blockIdx.x == 0 && t == 0 && hf == 0 && r == 0 && st < 64;
+                if (tr) a.trace[st * 8 + 2] = clock64();
                 mbar_wait(&d_ready[t], phase);
                 phase ^= 1;
                 tc_fence_after();
+                if (tr) a.trace[st * 8 + 3] = clock64();
 
-                f2 dx2[C / 2];
-                {
-                    const float4* dsrc = reinterpret_cast<const float4*>(dxs + (size_t)(st & 1) * kTile * 8);
-                    const float4 p0 = dsrc[0], p1 = dsrc[1];
-                    dx2[0] = pk(p0.x, p0.y); dx2[1] = pk(p0.z, p0.w); dx2[2] = pk(p1.x, p1.y); dx2[3] = pk(p1.z, p1.w);
-                }
-                // kv[h] = sum_c (D[h*C + c] + bias[h*C + c]) * dX[c]; 16 columns (2 hidden units) per TMEM load,
-                // the next load in flight while the current one is consumed
-                float kv[kHalf];
+                // ---- critical path: kv[h] += sum_c D[h*C + c] * dX[c] ---------------------------------
                 uint32_t va[16], vb[16];
                 tmem_ld16_issue(taddr, va);
 #pragma unroll
@@ -689,57 +698,57 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     if (j + 1 < kHalf / 2) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const float4 q0 = *reinterpret_cast<const float4*>(bias_h + 16 * j + C * hh);
-                        const float4 q1 = *reinterpret_cast<const float4*>(bias_h + 16 * j + C * hh + 4);
-                        f2 acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 0]), __uint_as_float(cur[C * hh + 1])), pk(q0.x, q0.y)), dx2[0], pk(0.f, 0.f));
-                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 2]), __uint_as_float(cur[C * hh + 3])), pk(q0.z, q0.w)), dx2[1], acc);
-                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 4]), __uint_as_float(cur[C * hh + 5])), pk(q1.x, q1.y)), dx2[2], acc);
-                        acc = fma2(add2(pk(__uint_as_float(cur[C * hh + 6]), __uint_as_float(cur[C * hh + 7])), pk(q1.z, q1.w)), dx2[3], acc);
+                        f2 acc = mul2(pk(__uint_as_float(cur[C * hh + 0]), __uint_as_float(cur[C * hh + 1])), dx2[0]);
+                        acc = fma2(pk(__uint_as_float(cur[C * hh + 2]), __uint_as_float(cur[C * hh + 3])), dx2[1], acc);
+                        acc = fma2(pk(__uint_as_float(cur[C * hh + 4]), __uint_as_float(cur[C * hh + 5])), dx2[2], acc);
+                        acc = fma2(pk(__uint_as_float(cur[C * hh + 6]), __uint_as_float(cur[C * hh + 7])), dx2[3], acc);
                         float lo, hi;
                         upk(acc, lo, hi);
-                        const float sum = lo + hi;
-                        kv[2 * j + hh] = (a.sign < 0.f) ? -sum : sum;
+                        const float sum = kv[2 * j + hh] + (lo + hi);
+                        kv[2 * j + hh] = negate ? -sum : sum;
                     }
                 }
 
-                // Runge-Kutta combination, one rounding per operation, two hidden units per instruction
+                if (tr) a.trace[st * 8 + 4] = clock64();
+                // ---- Runge-Kutta combination, one rounding per operation, two hidden units per instruction
                 bool step_done = false;
-                float zn[kHalf];
+                float zn[kHalf], y[kHalf], k1[kHalf];
+#pragma unroll
+                for (int h = 0; h < kHalf; ++h) y[h] = ypark[(size_t)h * kTile];
                 const f2 dt2 = pk(dt, dt);
                 if (a.method == TCDE_RK4_38) {
                     const f2 th2 = pk(third, third);
+                    if (sub != 0) {
+#pragma unroll
+                        for (int h = 0; h < kHalf; ++h) k1[h] = kpark[(size_t)h * kTile];
+                    }
                     if (sub == 0) {
 #pragma unroll
-                        for (int h = 0; h < kHalf; h += 2) {
-                            park[(size_t)h * kTile] = kv[h];
-                            park[(size_t)(h + 1) * kTile] = kv[h + 1];
-                            const f2 k1 = pk(kv[h], kv[h + 1]);
-                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, k1), th2)), zn[h], zn[h + 1]);
-                        }
+                        for (int h = 0; h < kHalf; h += 2)
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, pk(kv[h], kv[h + 1])), th2)), zn[h], zn[h + 1]);
+#pragma unroll
+                        for (int h = 0; h < kHalf; ++h) kpark[(size_t)h * kTile] = kv[h];
                     } else if (sub == 1) {
 #pragma unroll
                         for (int h = 0; h < kHalf; h += 2) {
-                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
                             const f2 k2 = pk(kv[h], kv[h + 1]);
                             s23[h] = kv[h];
                             s23[h + 1] = kv[h + 1];
-                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(k2, mul2(k1, th2)))), zn[h], zn[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(k2, mul2(pk(k1[h], k1[h + 1]), th2)))), zn[h], zn[h + 1]);
                         }
                     } else if (sub == 2) {
 #pragma unroll
                         for (int h = 0; h < kHalf; h += 2) {
-                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
                             const f2 k2 = pk(s23[h], s23[h + 1]);
                             const f2 k3 = pk(kv[h], kv[h + 1]);
-                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(k1, k2), k3))), zn[h], zn[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(pk(k1[h], k1[h + 1]), k2), k3))), zn[h], zn[h + 1]);
                             upk(add2(k2, k3), s23[h], s23[h + 1]);
                         }
                     } else {
                         const f2 three = pk(3.f, 3.f), eighth = pk(0.125f, 0.125f);
 #pragma unroll
                         for (int h = 0; h < kHalf; h += 2) {
-                            const f2 k1 = pk(park[(size_t)h * kTile], park[(size_t)(h + 1) * kTile]);
-                            const f2 sum = add2(add2(k1, mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
+                            const f2 sum = add2(add2(pk(k1[h], k1[h + 1]), mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
                             upk(add2(pk(y[h], y[h + 1]), mul2(mul2(sum, dt2), eighth)), zn[h], zn[h + 1]);
                         }
                         step_done = true;
@@ -759,33 +768,32 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
                     step_done = true;
                 }
-                if (step_done) {
+                if (tr) a.trace[st * 8 + 5] = clock64();
+                if (more) write_a(zn);                    // hand the next stage to the tensor core first ...
+                if (tr) a.trace[st * 8 + 6] = clock64();
+                if (step_done) {                          // ... then the bookkeeping that nobody waits for
                     while (next_out == step) {
                         const int mode = a.out_mode[jn];
                         if (mode == 0) write_out(jn, y);
                         else if (mode == 1) write_out(jn, zn);
                         else {
-                            const float slope = a.out_slope[jn];
+                            const float slope_w = a.out_slope[jn];
                             float v[kHalf];
 #pragma unroll
-                            for (int h = 0; h < kHalf; ++h) v[h] = E::add(y[h], E::mul(slope, E::sub(zn[h], y[h])));
+                            for (int h = 0; h < kHalf; ++h) v[h] = E::add(y[h], E::mul(slope_w, E::sub(zn[h], y[h])));
                             write_out(jn, v);
                         }
                         ++jn;
                         next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
                     }
 #pragma unroll
-                    for (int h = 0; h < kHalf; ++h) y[h] = zn[h];
+                    for (int h = 0; h < kHalf; ++h) ypark[(size_t)h * kTile] = zn[h];
                     ++step;
                     sub = 0;
                     dt = dt_next;
                     if (step + 1 < a.n_steps) dt_next = a.step_dt[step + 1];
                 } else {
                     ++sub;
-                }
-                if (more) {
-                    if (hf == 0) publish_dx(frac_n, (st + 1) & 1);
-                    write_a(zn);
                 }
             }
         }
