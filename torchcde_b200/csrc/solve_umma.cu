@@ -481,7 +481,11 @@ template <int N> struct Smem2 {
     static constexpr int a_lo = a_hi + kTiles * kTile * 128;
     static constexpr int bias = a_lo + kTiles * kTile * 128;             // [N] floats
     static constexpr int park = bias + N * 4;                            // [2 (y, k1)][kTiles][kH][kTile] floats
-    static constexpr int bars = park + 2 * kTiles * kH * kTile * 4;
+    // bias as a 13th MMA: A_aug[128][8] = (1, 1, 0, ...) and B_aug[N][8] = (bias_hi, bias_lo, 0, ...),
+    // K-major WITHOUT swizzle: 8-row x 16-byte core matrices, k 4..7 at +128 B, next 8 rows at +256 B
+    static constexpr int a_aug = park + 2 * kTiles * kH * kTile * 4;     // 128 rows x 32 B
+    static constexpr int b_aug = a_aug + kTile * 32;                     // N rows x 32 B
+    static constexpr int bars = b_aug + N * 32;
     static constexpr int total = bars + 64;
 };
 
@@ -514,6 +518,20 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
         b_lo[swz(n, k)] = w - hi;
     }
     for (int e = tid; e < N; e += kThreads2) bias_s[e] = a.bias[e];
+    {
+        float* a_aug = reinterpret_cast<float*>(smem + S::a_aug);
+        float* b_aug = reinterpret_cast<float*>(smem + S::b_aug);
+        for (int e = tid; e < kTile * 8; e += kThreads2) {
+            const int row = e >> 3, k = e & 7;
+            a_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k < 2) ? 1.f : 0.f;
+        }
+        for (int e = tid; e < N * 8; e += kThreads2) {
+            const int row = e >> 3, k = e & 7;
+            const float b = a.bias[row];
+            const float hi = tf32_hi(b);
+            b_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k == 0) ? hi : (k == 1) ? (b - hi) : 0.f;
+        }
+    }
     if (tid == 0) {
         for (int t = 0; t < kTiles; ++t) {
             mbar_init(&a_ready[t], 2 * kTile);
@@ -535,6 +553,10 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
     if (warp == kMmaWarp) {
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
         const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+        // no-swizzle K-major descriptors: LBO = 128 B (next 4 k), SBO = 256 B (next 8 rows), version 1, layout 0
+        const uint64_t aug_fields = (8ull << 16) | (16ull << 32) | (1ull << 46);
+        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | aug_fields;
+        const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | aug_fields;
         uint32_t phase[kTiles] = {0, 0};
         for (int st = 0; st < total; ++st) {
 #pragma unroll
@@ -555,6 +577,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
+                        mma_tf32(d, da_aug, db_aug, idesc, 1);            // + bias (as 1 * bias_hi + 1 * bias_lo)
                     } else {
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
@@ -575,7 +598,6 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
         if (tile_live[t]) {
             float* a_hi = reinterpret_cast<float*>(smem + S::a_hi + t * kTile * 128);
             float* a_lo = reinterpret_cast<float*>(smem + S::a_lo + t * kTile * 128);
-            const float* bias_h = bias_s + hf * kHalf * C;
             // y and k1 are parked in shared memory ([h][row]: conflict-free) between stages: with 544
             // threads the register file allows 96 registers per thread, and only the Runge-Kutta
             // phase needs them (all loads first, then the arithmetic, then the stores)
@@ -668,19 +690,6 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     frac0 = a.stage_frac[st + 1];
                 }
                 float kv[kHalf];
-#pragma unroll
-                for (int h = 0; h < kHalf; ++h) {
-                    const float4 q0 = *reinterpret_cast<const float4*>(bias_h + C * h);
-                    const float4 q1 = *reinterpret_cast<const float4*>(bias_h + C * h + 4);
-                    f2 acc = mul2(pk(q0.x, q0.y), dx2[0]);
-                    acc = fma2(pk(q0.z, q0.w), dx2[1], acc);
-                    acc = fma2(pk(q1.x, q1.y), dx2[2], acc);
-                    acc = fma2(pk(q1.z, q1.w), dx2[3], acc);
-                    float lo, hi;
-                    upk(acc, lo, hi);
-                    kv[h] = lo + hi;
-                }
-
                 const bool tr = a.trace && blockIdx.x == 0 && t == 0 && hf == 0 && r == 0 && st < 64;
                 if (tr) a.trace[st * 8 + 2] = clock64();
                 mbar_wait(&d_ready[t], phase);
@@ -704,7 +713,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                         acc = fma2(pk(__uint_as_float(cur[C * hh + 6]), __uint_as_float(cur[C * hh + 7])), dx2[3], acc);
                         float lo, hi;
                         upk(acc, lo, hi);
-                        const float sum = kv[2 * j + hh] + (lo + hi);
+                        const float sum = lo + hi;
                         kv[2 * j + hh] = negate ? -sum : sum;
                     }
                 }
