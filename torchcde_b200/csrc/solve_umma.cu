@@ -454,22 +454,18 @@ __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
-// 32 lanes x 16 columns
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
+// 32 lanes x 8 columns (= the 8 channels of one hidden unit)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 // Wait for this thread's outstanding tcgen05.ld.  The destination registers are passed through the
 // statement ("+r") so that the compiler cannot schedule any use of them above the wait.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                  :
                  : "memory");
 }
@@ -489,7 +485,7 @@ template <int N> struct Smem2 {
     static constexpr int total = bars + 64;
 };
 
-template <int C>
+template <int C, bool TRACE>
 __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaArgs a) {
     constexpr int N = kH * C;
     static_assert(C == 8 && N == 256, "written for 8 channels x 32 hidden units");
@@ -569,7 +565,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                     const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
-                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                     if (a.split_terms == 3) {
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
@@ -583,7 +579,7 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
                     }
                     mma_commit(&d_ready[t]);
-                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             }
@@ -688,9 +684,11 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                 if (more) {                               // next stage's schedule entry: a full stage of latency hiding
                     idx0 = a.stage_index[st + 1];
                     frac0 = a.stage_frac[st + 1];
+                    // ... and its spline row: pull the 128-byte line towards L1/L2 now, consume it a stage later
+                    if (hf == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(crow + (size_t)idx0 * (row_stride / 4)));
                 }
                 float kv[kHalf];
-                const bool tr = a.trace && blockIdx.x == 0 && t == 0 && hf == 0 && r == 0 && st < 64;
+                const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && hf == 0 && r == 0 && st < 64;
                 if (tr) a.trace[st * 8 + 2] = clock64();
                 mbar_wait(&d_ready[t], phase);
                 phase ^= 1;
@@ -698,24 +696,21 @@ __global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaAr
                 if (tr) a.trace[st * 8 + 3] = clock64();
 
                 // ---- critical path: kv[h] += sum_c D[h*C + c] * dX[c] ---------------------------------
-                uint32_t va[16], vb[16];
-                tmem_ld16_issue(taddr, va);
+                uint32_t va[8], vb[8];
+                tmem_ld8_issue(taddr, va);
 #pragma unroll
-                for (int j = 0; j < kHalf / 2; ++j) {
-                    uint32_t* cur = (j & 1) ? vb : va;
+                for (int h = 0; h < kHalf; ++h) {
+                    uint32_t* cur = (h & 1) ? vb : va;
                     tmem_ld_wait(cur);
-                    if (j + 1 < kHalf / 2) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        f2 acc = mul2(pk(__uint_as_float(cur[C * hh + 0]), __uint_as_float(cur[C * hh + 1])), dx2[0]);
-                        acc = fma2(pk(__uint_as_float(cur[C * hh + 2]), __uint_as_float(cur[C * hh + 3])), dx2[1], acc);
-                        acc = fma2(pk(__uint_as_float(cur[C * hh + 4]), __uint_as_float(cur[C * hh + 5])), dx2[2], acc);
-                        acc = fma2(pk(__uint_as_float(cur[C * hh + 6]), __uint_as_float(cur[C * hh + 7])), dx2[3], acc);
-                        float lo, hi;
-                        upk(acc, lo, hi);
-                        const float sum = lo + hi;
-                        kv[2 * j + hh] = negate ? -sum : sum;
-                    }
+                    if (h + 1 < kHalf) tmem_ld8_issue(taddr + (uint32_t)(C * (h + 1)), (h & 1) ? va : vb);
+                    f2 acc = mul2(pk(__uint_as_float(cur[0]), __uint_as_float(cur[1])), dx2[0]);
+                    acc = fma2(pk(__uint_as_float(cur[2]), __uint_as_float(cur[3])), dx2[1], acc);
+                    acc = fma2(pk(__uint_as_float(cur[4]), __uint_as_float(cur[5])), dx2[2], acc);
+                    acc = fma2(pk(__uint_as_float(cur[6]), __uint_as_float(cur[7])), dx2[3], acc);
+                    float lo, hi;
+                    upk(acc, lo, hi);
+                    const float sum = lo + hi;
+                    kv[h] = negate ? -sum : sum;
                 }
 
                 if (tr) a.trace[st * 8 + 4] = clock64();
@@ -832,7 +827,7 @@ int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t st
         TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
     } else {
-        auto kern = umma::v2::cdeint_umma2_kernel<8>;
+        auto kern = a.trace ? umma::v2::cdeint_umma2_kernel<8, true> : umma::v2::cdeint_umma2_kernel<8, false>;
         constexpr int smem = umma::v2::Smem2<256>::total + 1024;
         TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<(unsigned)ctas, umma::v2::kThreads2, smem, stream>>>(a);
