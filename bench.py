@@ -287,6 +287,7 @@ def run_gpu_arm(args):
         e2e_ms = time_loop(e2e_step, e2e_steps, 1, device, dist)
         torch.cuda.synchronize(device)
         e2e_ok = torch.equal(out_host.to(device), holder["out"])
+        e2e_h2d = coeffs_host.numel() * 4 + z0_host.numel() * 4
         del coeffs_host, pipe
 
         # the same result from the RAW series on the host (coefficients rebuilt on the device)
@@ -356,7 +357,7 @@ def run_gpu_arm(args):
                                "hid=32, adjoint=False", "parallelism": "batch-sharded x{}".format(world),
                    "global_batch": world * BATCH, "l2": "inputs (2.1 GB coeffs per GPU) exceed the 126 MB L2; no flush"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": coeffs_host.numel() * 4 + z0_host.numel() * 4,
+        "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "torchcde_b200.hostio.cdeint_from_host (pinned host coeffs+z0 -> chunked H2D / fused solve / D2H "
                        "on 2 streams)", "matches_device_result": bool(e2e_ok),

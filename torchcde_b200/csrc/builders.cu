@@ -294,7 +294,18 @@ linear_fill_warp_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
         T* og = out + p * (int64_t)L * C;
         __syncwarp();
         const int di = 32 / C, dc = 32 - di * C;
-        {
+        const bool vec4 = (sizeof(T) == 4) && ((C & 3) == 0) && (32 % (C >> 2) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+        if (vec4) {                                         // 128-bit coalesced loads, transposed to [c][i]
+            const int Q = C >> 2, qi = 32 / Q;              // lane -> (row offset lane / Q, quad lane % Q)
+            const int q = lane % Q;
+            const float4* xg4 = reinterpret_cast<const float4*>(xg);
+            for (int i = lane / Q; i < L; i += qi) {
+                const float4 v4 = xg4[(size_t)i * Q + q];
+                T* dst = tile + (4 * q) * Lp + i;
+                dst[0] = (T)v4.x; dst[Lp] = (T)v4.y; dst[2 * Lp] = (T)v4.z; dst[3 * Lp] = (T)v4.w;
+            }
+        } else {
             int i = lane / C, c = lane - (lane / C) * C;
             for (int e = lane; e < L * C; e += 32) {        // coalesced load, transposed to [c][i]
                 tile[c * Lp + i] = xg[e];
@@ -331,44 +342,49 @@ linear_fill_warp_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
             }
             const T v_first = row[first], v_last = row[last];
             __syncwarp();
+            // first observation in any LATER round, per round (one backward pass instead of a search per round)
+            int later_first[kFillRounds];
+            {
+                int carry = L;
+#pragma unroll
+                for (int k = kFillRounds - 1; k >= 0; --k) {
+                    later_first[k] = carry;
+                    if (m[k]) carry = 32 * k + __ffs(m[k]) - 1;
+                }
+            }
             int carry_prev = -1;
+            const uint32_t le_mask = 0xffffffffu >> (31 - lane);
 #pragma unroll
             for (int k = 0; k < kFillRounds; ++k) {
                 const int i = 32 * k + lane;
-                const bool inside = (k < rounds) && (i < L);
-                const bool hole = inside && is_nan(v[k]);
-                // nearest observation at or before / at or after position i
-                const uint32_t below = m[k] & (0xffffffffu >> (31 - lane));
-                int prv = below ? 32 * k + 31 - __clz(below) : carry_prev;
-                const uint32_t above = m[k] >> lane;
-                int nxt = L;
-                if (above) nxt = 32 * k + lane + __ffs(above) - 1;
-                else {
-#pragma unroll
-                    for (int k2 = kFillRounds - 1; k2 >= 0; --k2)
-                        if (k2 > k && m[k2]) nxt = 32 * k2 + __ffs(m[k2]) - 1;
+                const bool hole = (k < rounds) && (i < L) && is_nan(v[k]);
+                if (__any_sync(0xffffffffu, hole)) {        // whole rounds without a gap are skipped (warp-uniform)
+                    const uint32_t below = m[k] & le_mask;
+                    const int prv = below ? 32 * k + 31 - __clz(below) : carry_prev;
+                    const uint32_t above = m[k] >> lane;
+                    const int nxt = above ? i + __ffs(above) - 1 : later_first[k];
+                    if (hole) {
+                        int lo_i, hi_i;
+                        T lo_v, hi_v;
+                        if (prv < 0) {                      // before the first observation
+                            lo_i = 0; hi_i = first; lo_v = v_first; hi_v = v_first;
+                        } else if (nxt >= L) {              // after the last observation
+                            lo_i = last; hi_i = L - 1; lo_v = v_last; hi_v = v_last;
+                        } else {
+                            lo_i = prv; hi_i = nxt; lo_v = row[prv]; hi_v = row[nxt];
+                        }
+                        T filled;
+                        if (i == lo_i) filled = lo_v;       // an imputed end point itself
+                        else if (i == hi_i) filled = hi_v;
+                        else {
+                            const T tl = time_of(lo_i);
+                            const T ratio = E::div(E::sub(time_of(i), tl), E::sub(time_of(hi_i), tl));
+                            filled = E::add(lo_v, E::mul(ratio, E::sub(hi_v, lo_v)));
+                        }
+                        v[k] = filled;
+                    }
                 }
                 if (m[k]) carry_prev = 32 * k + 31 - __clz(m[k]);
-                if (hole) {
-                    int lo_i, hi_i;
-                    T lo_v, hi_v;
-                    if (prv < 0) {                          // before the first observation
-                        lo_i = 0; hi_i = first; lo_v = v_first; hi_v = v_first;
-                    } else if (nxt >= L) {                  // after the last observation
-                        lo_i = last; hi_i = L - 1; lo_v = v_last; hi_v = v_last;
-                    } else {
-                        lo_i = prv; hi_i = nxt; lo_v = row[prv]; hi_v = row[nxt];
-                    }
-                    T filled;
-                    if (i == lo_i) filled = lo_v;           // an imputed end point itself
-                    else if (i == hi_i) filled = hi_v;
-                    else {
-                        const T tl = time_of(lo_i);
-                        const T ratio = E::div(E::sub(time_of(i), tl), E::sub(time_of(hi_i), tl));
-                        filled = E::add(lo_v, E::mul(ratio, E::sub(hi_v, lo_v)));
-                    }
-                    v[k] = filled;
-                }
             }
             __syncwarp();                                   // every gather from row[] is done
 #pragma unroll
@@ -376,7 +392,15 @@ linear_fill_warp_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
                 if (k < rounds && 32 * k + lane < L) row[32 * k + lane] = v[k];
         }
         __syncwarp();
-        {
+        if (vec4) {
+            const int Q = C >> 2, qi = 32 / Q;
+            const int q = lane % Q;
+            float4* og4 = reinterpret_cast<float4*>(og);
+            for (int i = lane / Q; i < L; i += qi) {
+                const T* src = tile + (4 * q) * Lp + i;
+                og4[(size_t)i * Q + q] = make_float4((float)src[0], (float)src[Lp], (float)src[2 * Lp], (float)src[3 * Lp]);
+            }
+        } else {
             int i = lane / C, c = lane - (lane / C) * C;
             for (int e = lane; e < L * C; e += 32) {
                 og[e] = tile[c * Lp + i];
@@ -523,12 +547,28 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
     const int n_chunks = (L + G - 1) / G;
     const int n_items = C * n_chunks;
     const int di = kThreads / C, dc = kThreads - di * C;
+    const bool vec4 = (sizeof(T) == 4) && ((C & 3) == 0) && L > 2 && use_bulk &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     bool saw_nan = false;
     int buf = 0;
 
     for (int64_t p = blockIdx.x; p < n_paths; p += gridDim.x) {
         __syncthreads();                 // the previous path's coefficient phase is done with xs / ks
-        {
+        if (vec4) {                      // 128-bit coalesced loads, transposed to [c][i]
+            const float4* xg4 = reinterpret_cast<const float4*>(x + p * (int64_t)L * C);
+            const int Q = C >> 2;
+            int i = tid / Q, q = tid - (tid / Q) * Q;
+            const int dq_i = kThreads / Q, dq_q = kThreads - dq_i * Q;
+            for (int e = tid; e < L * Q; e += kThreads) {
+                const float4 v4 = xg4[e];
+                saw_nan |= is_nan(v4.x) | is_nan(v4.y) | is_nan(v4.z) | is_nan(v4.w);
+                T* dst = xs + (4 * q) * Lp + i;
+                dst[0] = (T)v4.x; dst[Lp] = (T)v4.y; dst[2 * Lp] = (T)v4.z; dst[3 * Lp] = (T)v4.w;
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+        } else {
             const T* xg = x + p * (int64_t)L * C;
             int i = tid / C, c = tid - (tid / C) * C;
             for (int e = tid; e < L * C; e += kThreads) {
@@ -582,8 +622,45 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
             if (use_bulk && tid == 0) bulk_wait_read<1>();
             __syncthreads();
             T* ot = buf ? ot1 : ot0;
+            if (vec4) {                  // (interval, 4 channels) per thread, 128-bit staged stores
+                const int Q = C >> 2;
+                float4* ot4 = reinterpret_cast<float4*>(ot);
+                int i = tid / Q, q = tid - (tid / Q) * Q;
+                const int dq_i = kThreads / Q, dq_q = kThreads - dq_i * Q;
+                for (int e = tid; e < nr * Q; e += kThreads) {
+                    const int r = r0 + i;
+                    const T rd = rdt[r], rd2 = rdt2[r];
+                    float av[4], bv[4], cv[4], dv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const T* xr = xs + (4 * q + j) * Lp + r;
+                        const T* kr = ks + (4 * q + j) * Lp + r;
+                        const T xl = xr[0], xh = xr[1], kl = kr[0], kh = kr[1];
+                        const T six = E::mul(T(2), E::mul(T(3), E::sub(xh, xl)));
+                        const T sr = E::mul(six, rd);
+                        av[j] = (float)xl;
+                        bv[j] = (float)kl;
+                        cv[j] = (float)E::mul(E::sub(E::sub(sr, E::mul(T(4), kl)), E::mul(T(2), kh)), rd);
+                        dv[j] = (float)E::mul(E::add(-sr, E::mul(T(3), E::add(kl, kh))), rd2);
+                    }
+                    float4* row = ot4 + (size_t)i * (4 * Q) + q;
+#pragma unroll
+                    for (int kq = 0; kq < 4; ++kq) {
+                        const int w = (kq + i) & 3;
+                        float4 v;
+                        if (w == 0) v = make_float4(av[0], av[1], av[2], av[3]);
+                        else if (w == 1) v = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                        else if (w == 2) v = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                        else v = make_float4(dv[0], dv[1], dv[2], dv[3]);
+                        row[w * Q] = v;
+                    }
+                    i += dq_i;
+                    q += dq_q;
+                    if (q >= Q) { q -= Q; ++i; }
+                }
+            }
             int i = tid / C, c = tid - (tid / C) * C;
-            for (int e = tid; e < nr * C; e += kThreads) {
+            for (int e = vec4 ? nr * C : tid; e < nr * C; e += kThreads) {
                 const int r = r0 + i;
                 const T* xr = xs + c * Lp + r;
                 const T* kr = ks + c * Lp + r;
