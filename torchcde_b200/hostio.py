@@ -9,7 +9,7 @@ SMs work at the same time.  Paths are independent, so chunking does not change a
 """
 import torch
 
-from .coeffs import hermite_cubic_coefficients_with_backward_differences
+from . import _lib
 from .controls import CubicSpline, LinearInterpolation
 from .solver import cdeint
 
@@ -70,7 +70,8 @@ def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths
     (P, L, C)) in, build the Hermite backward-difference coefficients on the device
     (``hermite_cubic_coefficients_with_backward_differences``), solve, copy the result out.  Moving
     ``x`` instead of its coefficients cuts the PCIe traffic 4x; rebuilding the coefficients costs
-    ~0.5 ms per 65,536 paths on the device."""
+    ~0.5 ms per 65,536 paths on the device.  The series must be NaN-free (the NaN check of the public
+    builder needs a host read-back per chunk, which would serialise the pipeline); float32 / float64."""
     device = torch.device(device if device is not None else "cuda")
     n_paths, hidden = z0_host.shape
     n_out = t.numel()
@@ -94,7 +95,10 @@ def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths
                 z_dev = zs[slot][:hi - lo]
                 x_dev.copy_(x_host[lo:hi], non_blocking=True)
                 z_dev.copy_(z0_host[lo:hi], non_blocking=True)
-                coeffs = hermite_cubic_coefficients_with_backward_differences(x_dev)
+                n, length, channels = x_dev.shape
+                coeffs = torch.empty(n, length - 1, 4 * channels, dtype=x_dev.dtype, device=device)
+                _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(x_dev), None, _lib.ptr(coeffs), n, length, channels,
+                          _lib.dtype_code(x_dev.dtype), None, _lib.stream_of(x_dev))
                 out = cdeint(CubicSpline(coeffs), func, z_dev, t_cpu, **kwargs)
                 out_host[lo:hi].copy_(out, non_blocking=True)
     for s in streams:
