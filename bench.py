@@ -233,6 +233,11 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to fd 1) get
+    # stderr; the JSON is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -392,9 +397,10 @@ def run_gpu_arm(args):
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():

@@ -134,20 +134,75 @@ __device__ __forceinline__ float tf32_hi(float x) {
     return __uint_as_float(u);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, IEEE rounding per lane) ----------
+typedef uint64_t f2;
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+
+// 32 lanes x 32 columns, issue and wait separated so that the next load overlaps the arithmetic on
+// the current one.  The destination registers go through the wait statement ("+r") so that the
+// compiler cannot schedule a use above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
 // shared memory map (bytes)
 template <int N> struct Smem {
     static constexpr int b_hi = 0;
     static constexpr int b_lo = b_hi + N * 128;
     static constexpr int a_hi = b_lo + N * 128;                         // [kTiles][128 rows][128 B]
     static constexpr int a_lo = a_hi + kTiles * kTile * 128;
-    static constexpr int bias = a_lo + kTiles * kTile * 128;            // [N] floats
-    static constexpr int park = bias + N * 4;                           // [kTiles][2][kH][kTile] floats
+    static constexpr int park = a_lo + kTiles * kTile * 128;            // [kTiles][2][kH][kTile] floats
     static constexpr int raw = park + kTiles * 2 * kH * kTile * 4;      // [kTiles][6][kTile] float4
-    static constexpr int bars = raw + kTiles * 6 * kTile * 16;          // a_ready[2], d_ready[2], tmem slot
+    // bias as a 13th MMA (K augmentation), K-major without swizzle: B_aug[N][8] = (bias_hi, bias_lo, 0...);
+    // A_aug = (1, 1, 0...) for every row, so ONE 8-row core-matrix pair serves all 128 rows (SBO = 0)
+    static constexpr int b_aug = raw + kTiles * 6 * kTile * 16;         // N rows x 32 B
+    static constexpr int a_aug = b_aug + N * 32;                        // 8 rows x 32 B
+    static constexpr int bars = a_aug + 256;                            // a_ready[2], d_ready[2], tmem slot
     static constexpr int total = bars + 64;
 };
 
-template <int C>
+template <int C, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs a) {
     constexpr int N = kH * C;
     static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
@@ -159,7 +214,6 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     float* b_hi = reinterpret_cast<float*>(smem + S::b_hi);
     float* b_lo = reinterpret_cast<float*>(smem + S::b_lo);
-    float* bias_s = reinterpret_cast<float*>(smem + S::bias);
     uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
     uint64_t* d_ready = a_ready + kTiles;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
@@ -177,7 +231,20 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
         b_hi[swz(n, k)] = hi;
         b_lo[swz(n, k)] = w - hi;
     }
-    for (int e = tid; e < N; e += kThreads) bias_s[e] = a.bias[e];
+    {
+        float* a_aug = reinterpret_cast<float*>(smem + S::a_aug);
+        float* b_aug = reinterpret_cast<float*>(smem + S::b_aug);
+        for (int e = tid; e < 8 * 8; e += kThreads) {
+            const int row = e >> 3, k = e & 7;
+            a_aug[(k >> 2) * 32 + row * 4 + (k & 3)] = (k < 2) ? 1.f : 0.f;
+        }
+        for (int e = tid; e < N * 8; e += kThreads) {
+            const int row = e >> 3, k = e & 7;
+            const float bv = a.bias[row];
+            const float hi = tf32_hi(bv);
+            b_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k == 0) ? hi : (k == 1) ? (bv - hi) : 0.f;
+        }
+    }
     if (tid == 0) {
         for (int t = 0; t < kTiles; ++t) {
             mbar_init(&a_ready[t], kTile);
@@ -186,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
         fence_barrier_init();
     }
     if (warp == kTiles * 4) tmem_alloc(tmem_slot, 512);
-    fence_proxy_async_smem();                             // W tiles were written by the generic proxy
+    fence_proxy_async_smem();                             // operand tiles were written by the generic proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -200,6 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
         // ================================ MMA issuer ==========================================
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
         const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+        // no-swizzle K-major descriptors: LBO = 128 B (next 4 k), SBO = 256 B (next 8 rows; 0 for A_aug:
+        // all rows are the same (1, 1, 0, ...)), version 1, layout type 0
+        const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (0ull << 32) | (1ull << 46);
         uint32_t phase[kTiles] = {0, 0};
         for (int st = 0; st < total; ++st) {
 #pragma unroll
@@ -209,10 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 phase[t] ^= 1;
                 tc_fence_after();
                 if ((tid & 31) == 0) {
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                     const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
-                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                     // small terms first; each k-block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
                     if (a.split_terms == 3) {
 #pragma unroll
@@ -225,8 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
                     }
+                    mma_tf32(d, da_aug, db_aug, idesc, 1);                // + bias (1 * bias_hi + 1 * bias_lo)
                     mma_commit(&d_ready[t]);
-                    if (a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             }
@@ -247,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
             const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
             const int row_stride = cubic ? 4 * C : C;
             const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0);
+            const bool negate = a.sign < 0.f;
 
             auto fetch_row = [&](int idx) {               // (b | 2c | 3d) of interval idx -> raw[0..5]
                 const float* src = crow + (int64_t)idx * row_stride;
@@ -258,10 +331,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float4 hi, lo;
-                    hi.x = tf32_hi(z[4 * c4 + 0]); lo.x = z[4 * c4 + 0] - hi.x;
-                    hi.y = tf32_hi(z[4 * c4 + 1]); lo.y = z[4 * c4 + 1] - hi.y;
-                    hi.z = tf32_hi(z[4 * c4 + 2]); lo.z = z[4 * c4 + 2] - hi.z;
-                    hi.w = tf32_hi(z[4 * c4 + 3]); lo.w = z[4 * c4 + 3] - hi.w;
+                    hi.x = tf32_hi(z[4 * c4 + 0]); hi.y = tf32_hi(z[4 * c4 + 1]);
+                    hi.z = tf32_hi(z[4 * c4 + 2]); hi.w = tf32_hi(z[4 * c4 + 3]);
+                    upk(sub2(pk(z[4 * c4 + 0], z[4 * c4 + 1]), pk(hi.x, hi.y)), lo.x, lo.y);
+                    upk(sub2(pk(z[4 * c4 + 2], z[4 * c4 + 3]), pk(hi.z, hi.w)), lo.z, lo.w);
                     const uint32_t off = (uint32_t)r * 32u + (uint32_t)((c4 ^ (r & 7)) << 2);
                     *reinterpret_cast<float4*>(a_hi + off) = hi;
                     *reinterpret_cast<float4*>(a_lo + off) = lo;
@@ -287,91 +360,131 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 }
             }
             int jn = 0;
-            while (jn < a.n_out && a.out_step[jn] < 0) { write_out(jn, y); ++jn; }
+            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
+            while (jn < a.n_out && next_out < 0) {
+                write_out(jn, y);
+                ++jn;
+                next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+            }
             fetch_row(a.stage_index[0]);
             write_a(y);
 
             const float third = (float)(1.0 / 3.0);
             int step = 0, sub = 0;
             float dt = a.step_dt[0];
+            float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
+            float frac0 = a.stage_frac[0];                        // this stage's fraction
+            int idx1 = (total > 1) ? a.stage_index[1] : 0;        // next stage's schedule entry
+            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;
             uint32_t phase = 0;
             for (int st = 0; st < total; ++st) {
                 const bool more = st + 1 < total;
-                // dX/dt of this stage from the prefetched row (interpolation_cubic.py:331-336)
-                const float frac = a.stage_frac[st];
+                // ---- in the MMA's shadow: dX/dt from the prefetched row (interpolation_cubic.py:331-336) ----
                 cp_async_wait<0>();
-                float dx[C];
+                f2 dx2[C / 2];
                 {
                     const float4 b0 = raw[0], b1 = raw[kTile];
                     if (cubic) {
                         const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            dx[c] = E::add(bb[c], E::mul(E::add(cc[c], E::mul(dd[c], frac)), frac));
+                        const f2 fr = pk(frac0, frac0);
+                        dx2[0] = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr));
+                        dx2[1] = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr));
+                        dx2[2] = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr));
+                        dx2[3] = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr));
                     } else {
-                        dx[0] = b0.x; dx[1] = b0.y; dx[2] = b0.z; dx[3] = b0.w;
-                        dx[4] = b1.x; dx[5] = b1.y; dx[6] = b1.z; dx[7] = b1.w;
+                        dx2[0] = pk(b0.x, b0.y); dx2[1] = pk(b0.z, b0.w); dx2[2] = pk(b1.x, b1.y); dx2[3] = pk(b1.z, b1.w);
                     }
                 }
-                if (more) fetch_row(a.stage_index[st + 1]);
+                if (more) fetch_row(idx1);
+                frac0 = frac1;
+                if (st + 2 < total) {                     // schedule entries are read a full stage ahead
+                    idx1 = a.stage_index[st + 2];
+                    frac1 = a.stage_frac[st + 2];
+                }
 
-                const bool tr = a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
+                const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
                 if (tr) a.trace[st * 8 + 2] = clock64();
                 mbar_wait(&d_ready[t], phase);
                 phase ^= 1;
                 tc_fence_after();
                 if (tr) a.trace[st * 8 + 3] = clock64();
 
-                // kv[h] = sum_c (D[h*C + c] + bias[h*C + c]) * dX[c]
+                // ---- kv[h] = sum_c D[h*C + c] * dX[c]  (the bias is already in D); packed FFMA2, next TMEM
+                //      load in flight while the current 32 columns are consumed
                 float kv[kH];
+                {
+                    uint32_t va[16], vb[16];
+                    tmem_ld16_issue(taddr, va);
 #pragma unroll
-                for (int j = 0; j < N / 32; ++j) {
-                    float v[32];
-                    tmem_ld32(taddr + (uint32_t)(32 * j), v);
+                    for (int j = 0; j < N / 16; ++j) {
+                        uint32_t* cur = (j & 1) ? vb : va;
+                        tmem_ld16_wait(cur);
+                        if (j + 1 < N / 16) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
 #pragma unroll
-                    for (int hh = 0; hh < 32 / C; ++hh) {
-                        const float4 q0 = *reinterpret_cast<const float4*>(bias_s + 32 * j + C * hh);
-                        const float4 q1 = *reinterpret_cast<const float4*>(bias_s + 32 * j + C * hh + 4);
-                        const float bq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        float acc = 0.f;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) acc = fmaf(v[C * hh + c] + bq[c], dx[c], acc);
-                        kv[(32 / C) * j + hh] = (a.sign < 0.f) ? -acc : acc;
+                        for (int hh = 0; hh < 2; ++hh) {
+                            f2 acc = mul2(pk(__uint_as_float(cur[8 * hh + 0]), __uint_as_float(cur[8 * hh + 1])), dx2[0]);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 2]), __uint_as_float(cur[8 * hh + 3])), dx2[1], acc);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 4]), __uint_as_float(cur[8 * hh + 5])), dx2[2], acc);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 6]), __uint_as_float(cur[8 * hh + 7])), dx2[3], acc);
+                            float lo, hi;
+                            upk(acc, lo, hi);
+                            const float sum = lo + hi;
+                            kv[2 * j + hh] = negate ? -sum : sum;
+                        }
                     }
                 }
 
                 if (tr) a.trace[st * 8 + 4] = clock64();
-                // Runge-Kutta combination, one rounding per operation (oracle/odeint_port.py)
+                // ---- Runge-Kutta combination, one rounding per operation (oracle/odeint_port.py), two hidden
+                //      units per instruction; parked slopes are all loaded first, then combined, then stored
                 bool step_done = false;
                 float zn[kH];
+                const f2 dt2 = pk(dt, dt);
                 if (a.method == TCDE_RK4_38) {
+                    const f2 th2 = pk(third, third);
                     if (sub == 0) {
 #pragma unroll
-                        for (int h = 0; h < kH; ++h) {
-                            park[(size_t)h * kTile] = kv[h];
-                            zn[h] = E::add(y[h], E::mul(E::mul(dt, kv[h]), third));
-                        }
+                        for (int h = 0; h < kH; h += 2)
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, pk(kv[h], kv[h + 1])), th2)), zn[h], zn[h + 1]);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) park[(size_t)h * kTile] = kv[h];
                     } else if (sub == 1) {
+                        float k1[kH];
 #pragma unroll
-                        for (int h = 0; h < kH; ++h) {
-                            park[(size_t)(kH + h) * kTile] = kv[h];
-                            zn[h] = E::add(y[h], E::mul(dt, E::sub(kv[h], E::mul(park[(size_t)h * kTile], third))));
-                        }
+                        for (int h = 0; h < kH; ++h) k1[h] = park[(size_t)h * kTile];
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2)
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(pk(kv[h], kv[h + 1]), mul2(pk(k1[h], k1[h + 1]), th2)))),
+                                zn[h], zn[h + 1]);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) park[(size_t)(kH + h) * kTile] = kv[h];
                     } else if (sub == 2) {
+                        float k1[kH], k2[kH];
 #pragma unroll
                         for (int h = 0; h < kH; ++h) {
-                            const float k2 = park[(size_t)(kH + h) * kTile];
-                            zn[h] = E::add(y[h], E::mul(dt, E::add(E::sub(park[(size_t)h * kTile], k2), kv[h])));
-                            park[(size_t)(kH + h) * kTile] = E::add(k2, kv[h]);
+                            k1[h] = park[(size_t)h * kTile];
+                            k2[h] = park[(size_t)(kH + h) * kTile];
                         }
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            const f2 k2p = pk(k2[h], k2[h + 1]), k3p = pk(kv[h], kv[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(pk(k1[h], k1[h + 1]), k2p), k3p))), zn[h], zn[h + 1]);
+                            upk(add2(k2p, k3p), k2[h], k2[h + 1]);
+                        }
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) park[(size_t)(kH + h) * kTile] = k2[h];
                     } else {
+                        float k1[kH], s23[kH];
 #pragma unroll
                         for (int h = 0; h < kH; ++h) {
-                            const float sum = E::add(E::add(park[(size_t)h * kTile], E::mul(3.f, park[(size_t)(kH + h) * kTile])), kv[h]);
-                            zn[h] = E::add(y[h], E::mul(E::mul(sum, dt), 0.125f));
+                            k1[h] = park[(size_t)h * kTile];
+                            s23[h] = park[(size_t)(kH + h) * kTile];
+                        }
+                        const f2 three = pk(3.f, 3.f), eighth = pk(0.125f, 0.125f);
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            const f2 sum = add2(add2(pk(k1[h], k1[h + 1]), mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(sum, dt2), eighth)), zn[h], zn[h + 1]);
                         }
                         step_done = true;
                     }
@@ -390,31 +503,33 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     for (int h = 0; h < kH; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
                     step_done = true;
                 }
-                if (step_done) {
-                    while (jn < a.n_out && a.out_step[jn] == step) {
+                if (tr) a.trace[st * 8 + 5] = clock64();
+                if (more) write_a(zn);                    // hand the next stage to the tensor core first ...
+                if (tr) a.trace[st * 8 + 6] = clock64();
+                if (step_done) {                          // ... then the bookkeeping that nobody waits for
+                    while (next_out == step) {
                         const int mode = a.out_mode[jn];
                         if (mode == 0) write_out(jn, y);
                         else if (mode == 1) write_out(jn, zn);
                         else {
-                            const float slope = a.out_slope[jn];
+                            const float slope_w = a.out_slope[jn];
                             float v[kH];
 #pragma unroll
-                            for (int h = 0; h < kH; ++h) v[h] = E::add(y[h], E::mul(slope, E::sub(zn[h], y[h])));
+                            for (int h = 0; h < kH; ++h) v[h] = E::add(y[h], E::mul(slope_w, E::sub(zn[h], y[h])));
                             write_out(jn, v);
                         }
                         ++jn;
+                        next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
                     }
 #pragma unroll
                     for (int h = 0; h < kH; ++h) y[h] = zn[h];
                     ++step;
                     sub = 0;
-                    if (step < a.n_steps) dt = a.step_dt[step];
+                    dt = dt_next;
+                    if (step + 1 < a.n_steps) dt_next = a.step_dt[step + 1];
                 } else {
                     ++sub;
                 }
-                if (tr) a.trace[st * 8 + 5] = clock64();
-                if (more) write_a(zn);
-                if (tr) a.trace[st * 8 + 6] = clock64();
             }
         }
     }
@@ -422,7 +537,6 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
     __syncthreads();
     if (warp == kTiles * 4) tmem_dealloc(tmem_base, 512);
 }
-
 
 // =================================================================================================
 // Version 2: two row threads per path, nothing but registers on the post-MMA critical path.
@@ -444,15 +558,6 @@ namespace v2 {
 
 constexpr int kHalf = kH / 2;                       // hidden units per thread
 constexpr int kThreads2 = kTiles * kTile * 2 + 32;  // 544
-
-// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, IEEE rounding per lane) ----------
-typedef uint64_t f2;
-__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
 // 32 lanes x 8 columns (= the 8 channels of one hidden unit)
 __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
@@ -822,7 +927,7 @@ int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t st
     const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
     TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
     if (version == 1) {
-        auto kern = umma::cdeint_umma_kernel<8>;
+        auto kern = a.trace ? umma::cdeint_umma_kernel<8, true> : umma::cdeint_umma_kernel<8, false>;
         constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
         TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
