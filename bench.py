@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.file,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -269,7 +269,13 @@ def run_gpu_arm(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+            for _ in range(40):            # the timed region is only tens of ms: give nvidia-smi (20 ms period)
+                step()                     # the same kernel to look at for ~0.2 s around it
         ms = time_loop(step, args.steps, args.warmup, device, dist)
+        if rank == 0:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize(device)
         clocks = sampler.stop() if rank == 0 else None
         assert bool(torch.isfinite(holder["out"]).all())
 

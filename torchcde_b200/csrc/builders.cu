@@ -11,6 +11,14 @@ namespace tcde {
 
 static constexpr int kThreads = 256;
 
+// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2): two IEEE-rounded operations per instruction
+typedef uint64_t f2;
+__device__ __forceinline__ f2 pk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // =========================================================================================
 // Hermite cubic with backward differences  (interpolation_hermite_cubic_bdiff.py:5-44)
 // =========================================================================================
@@ -467,52 +475,62 @@ __global__ void natural_prep_kernel(const T* __restrict__ t, T* __restrict__ ws,
     T* rdt2 = ws + L;
     T* mult = ws + 2 * L;
     T* rnd = ws + 3 * L;
+    __shared__ int s_wf, s_wb;
     for (int i = threadIdx.x; i < L - 1; i += blockDim.x) {
         const T t0 = t ? t[i] : T(i), t1 = t ? t[i + 1] : T(i + 1);
         const T r = E::div(T(1), E::sub(t1, t0));
         rdt[i] = r;
         rdt2[i] = E::mul(r, r);
     }
+    if (threadIdx.x == 0) { s_wf = 0; s_wb = 0; }
     __syncthreads();
     if (threadIdx.x == 0) {
         rdt[L - 1] = T(0);
         rdt2[L - 1] = T(0);
         // diag[i] = 2 * (rdt[i] + rdt[i-1]) with the out-of-range terms absent (cubic.py:31-35)
         T nd = E::mul(T(2), rdt[0]);
-        // mult[0] is unused by the sweep; it carries t1 - t0 for the two-knot case (cubic.py:18)
-        mult[0] = E::sub(t ? t[1] : T(1), t ? t[0] : T(0));
+        T r_prev = rdt[0];
+        // mult[0] is unused by the sweeps (0); for two knots it carries t1 - t0 (cubic.py:18)
+        mult[0] = (L > 2) ? T(0) : E::sub(t ? t[1] : T(1), t ? t[0] : T(0));
         rnd[0] = E::div(T(1), nd);
         for (int i = 1; i < L; ++i) {
-            const T diag = E::mul(T(2), (i < L - 1) ? E::add(rdt[i], rdt[i - 1]) : E::add(T(0), rdt[i - 1]));
-            const T w = E::div(rdt[i - 1], nd);                  // misc.py:59
-            nd = E::sub(diag, E::mul(w, rdt[i - 1]));            // misc.py:60
+            const T r_cur = (i < L - 1) ? rdt[i] : T(0);
+            const T diag = E::mul(T(2), E::add(r_cur, r_prev));
+            const T w = E::div(r_prev, nd);                      // misc.py:59
+            nd = E::sub(diag, E::mul(w, r_prev));                // misc.py:60
             mult[i] = w;
             rnd[i] = E::div(T(1), nd);
+            r_prev = r_cur;
         }
-        // Window sizes for the parallel sweeps of natural_win_kernel: the forward recurrence
-        // f[i] = rhs[i] - mult[i] f[i-1] forgets f[i-w] by the factor prod |mult|, the backward one
-        // k[i] = (f[i] - rdt[i] k[i+1]) rnd[i] forgets k[i+w] by prod |rdt rnd|; both factors are
-        // ~0.27 per knot for a diagonally dominant system.  A window is long enough when that
-        // product is below eps/16 (or it reaches the end of the series, where the start is exact).
+    }
+    __syncthreads();
+    // Window sizes for the parallel sweeps of natural_win_kernel: the forward recurrence
+    // f[i] = rhs[i] - mult[i] f[i-1] forgets f[i-w] by the factor prod |mult|, the backward one
+    // k[i] = (f[i] - rdt[i] k[i+1]) rnd[i] forgets k[i+w] by prod |rdt rnd|; both factors are
+    // ~0.27 per knot for a diagonally dominant system.  A window is long enough when that
+    // product is below eps/16 (or it reaches the end of the series, where the start is exact).
+    if (L > 2) {
         const T tol = (sizeof(T) == 4) ? T(3.7e-9) : T(1.4e-17);
         int wf = 0, wb = 0;
-        if (L > 2) {
-            for (int i = 1; i < L; ++i) {
-                T prod = T(1);
-                int w = 0;
-                for (int j = i; j >= 1 && prod > tol; --j) { prod *= fabs(mult[j]); ++w; }
-                wf = max(wf, w);
-            }
-            for (int i = 0; i < L - 1; ++i) {
-                T prod = T(1);
-                int w = 0;
-                for (int j = i; j < L - 1 && prod > tol; ++j) { prod *= fabs(rdt[j] * rnd[j]); ++w; }
-                wb = max(wb, w);
-            }
-            mult[0] = T(0);
+        for (int i = 1 + threadIdx.x; i < L; i += blockDim.x) {
+            T prod = T(1);
+            int w = 0;
+            for (int j = i; j >= 1 && prod > tol; --j) { prod *= fabs(mult[j]); ++w; }
+            wf = max(wf, w);
         }
-        ws[4 * L] = T(wf);
-        ws[4 * L + 1] = T(wb);
+        for (int i = threadIdx.x; i < L - 1; i += blockDim.x) {
+            T prod = T(1);
+            int w = 0;
+            for (int j = i; j < L - 1 && prod > tol; ++j) { prod *= fabs(rdt[j] * rnd[j]); ++w; }
+            wb = max(wb, w);
+        }
+        atomicMax(&s_wf, wf);
+        atomicMax(&s_wb, wb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ws[4 * L] = T(s_wf);
+        ws[4 * L + 1] = T(s_wb);
     }
 }
 
@@ -582,37 +600,78 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
         }
         __syncthreads();
         if (L > 2) {
-            for (int it = tid; it < n_items; it += kThreads) {          // forward sweep, windowed
-                const int c = it % C, j = it / C;
-                const int g0 = j * G, g1 = min(g0 + G, L);
-                const T* xr = xs + c * Lp;
-                T* fr = fs + c * Lp;
-                T f = T(0);
-                int i = max(g0 - wf, 0);
-                T x_lo = xr[i], sc_prev = T(0);
-                if (i > 0) sc_prev = E::mul(E::mul(T(3), E::sub(x_lo, xr[i - 1])), rdt2[i - 1]);
-                for (; i < g1; ++i) {
-                    T sc = T(0);
-                    if (i < L - 1) {
-                        const T x_hi = xr[i + 1];
-                        sc = E::mul(E::mul(T(3), E::sub(x_hi, x_lo)), rdt2[i]);
-                        x_lo = x_hi;
+            // scaled differences sc[i] = 3 (x[i+1] - x[i]) / dt_i^2 (0 for the last knot), parked in ks
+            for (int e = tid; e < C * L; e += kThreads) {
+                const int c = e / L, i = e - c * L;
+                const T* xr = xs + c * Lp + i;
+                ks[c * Lp + i] = (i < L - 1) ? E::mul(E::mul(T(3), E::sub(xr[1], xr[0])), rdt2[i]) : T(0);
+            }
+            __syncthreads();
+            const bool pairs = (sizeof(T) == 4) && ((C & 1) == 0);
+            if (pairs) {
+                // two series per thread, packed arithmetic: half the instructions of the scalar sweeps
+                const int C2 = C >> 1;
+                const int n_pair_items = C2 * n_chunks;
+                for (int it = tid; it < n_pair_items; it += kThreads) {     // forward sweep (misc.py:58-61)
+                    const int c = 2 * (it % C2), j = it / C2;
+                    const int g0 = j * G, g1 = min(g0 + G, L);
+                    const float* s0 = reinterpret_cast<const float*>(ks) + c * Lp;
+                    float* f0 = reinterpret_cast<float*>(fs) + c * Lp;
+                    int i = max(g0 - wf, 0);
+                    f2 f = pk2(0.f, 0.f);
+                    f2 sc_prev = (i > 0) ? pk2(s0[i - 1], s0[Lp + i - 1]) : pk2(0.f, 0.f);
+                    for (; i < g1; ++i) {
+                        const f2 sc = pk2(s0[i], s0[Lp + i]);
+                        const float m = (float)mult[i];
+                        f = sub2(add2(sc, sc_prev), mul2(pk2(m, m), f));
+                        sc_prev = sc;
+                        if (i >= g0) upk2(f, f0[i], f0[Lp + i]);
                     }
-                    f = E::sub(E::add(sc, sc_prev), E::mul(mult[i], f));     // cubic.py:36-39, misc.py:61
-                    sc_prev = sc;
-                    if (i >= g0) fr[i] = f;
+                }
+            } else {
+                for (int it = tid; it < n_items; it += kThreads) {
+                    const int c = it % C, j = it / C;
+                    const int g0 = j * G, g1 = min(g0 + G, L);
+                    const T* sr = ks + c * Lp;
+                    T* fr = fs + c * Lp;
+                    int i = max(g0 - wf, 0);
+                    T f = T(0);
+                    T sc_prev = (i > 0) ? sr[i - 1] : T(0);
+                    for (; i < g1; ++i) {
+                        const T sc = sr[i];
+                        f = E::sub(E::add(sc, sc_prev), E::mul(mult[i], f));     // cubic.py:36-39, misc.py:61
+                        sc_prev = sc;
+                        if (i >= g0) fr[i] = f;
+                    }
                 }
             }
             __syncthreads();
-            for (int it = tid; it < n_items; it += kThreads) {          // back substitution, windowed
-                const int c = it % C, j = it / C;
-                const int g0 = j * G, g1 = min(g0 + G, L);
-                const T* fr = fs + c * Lp;
-                T* kr = ks + c * Lp;
-                T k = T(0);
-                for (int i = min(g1 - 1 + wb, L - 1); i >= g0; --i) {
-                    k = E::mul(E::sub(fr[i], E::mul(rdt[i], k)), rnd[i]);    // misc.py:63-65 (rdt[L-1] = 0)
-                    if (i < g1) kr[i] = k;
+            if (pairs) {
+                const int C2 = C >> 1;
+                const int n_pair_items = C2 * n_chunks;
+                for (int it = tid; it < n_pair_items; it += kThreads) {     // back substitution (misc.py:63-65)
+                    const int c = 2 * (it % C2), j = it / C2;
+                    const int g0 = j * G, g1 = min(g0 + G, L);
+                    const float* f0 = reinterpret_cast<const float*>(fs) + c * Lp;
+                    float* k0 = reinterpret_cast<float*>(ks) + c * Lp;
+                    f2 k = pk2(0.f, 0.f);
+                    for (int i = min(g1 - 1 + wb, L - 1); i >= g0; --i) {
+                        const float rd = (float)rdt[i], rn = (float)rnd[i];
+                        k = mul2(sub2(pk2(f0[i], f0[Lp + i]), mul2(pk2(rd, rd), k)), pk2(rn, rn));
+                        if (i < g1) upk2(k, k0[i], k0[Lp + i]);
+                    }
+                }
+            } else {
+                for (int it = tid; it < n_items; it += kThreads) {
+                    const int c = it % C, j = it / C;
+                    const int g0 = j * G, g1 = min(g0 + G, L);
+                    const T* fr = fs + c * Lp;
+                    T* kr = ks + c * Lp;
+                    T k = T(0);
+                    for (int i = min(g1 - 1 + wb, L - 1); i >= g0; --i) {
+                        k = E::mul(E::sub(fr[i], E::mul(rdt[i], k)), rnd[i]);    // misc.py:63-65 (rdt[L-1] = 0)
+                        if (i < g1) kr[i] = k;
+                    }
                 }
             }
         }
@@ -631,17 +690,21 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
                     const int r = r0 + i;
                     const T rd = rdt[r], rd2 = rdt2[r];
                     float av[4], bv[4], cv[4], dv[4];
+                    const f2 rdp = pk2((float)rd, (float)rd), rd2p = pk2((float)rd2, (float)rd2);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const T* xr = xs + (4 * q + j) * Lp + r;
-                        const T* kr = ks + (4 * q + j) * Lp + r;
-                        const T xl = xr[0], xh = xr[1], kl = kr[0], kh = kr[1];
-                        const T six = E::mul(T(2), E::mul(T(3), E::sub(xh, xl)));
-                        const T sr = E::mul(six, rd);
-                        av[j] = (float)xl;
-                        bv[j] = (float)kl;
-                        cv[j] = (float)E::mul(E::sub(E::sub(sr, E::mul(T(4), kl)), E::mul(T(2), kh)), rd);
-                        dv[j] = (float)E::mul(E::add(-sr, E::mul(T(3), E::add(kl, kh))), rd2);
+                    for (int j = 0; j < 4; j += 2) {              // two channels per packed instruction
+                        const float* xr0 = reinterpret_cast<const float*>(xs) + (4 * q + j) * Lp + r;
+                        const float* kr0 = reinterpret_cast<const float*>(ks) + (4 * q + j) * Lp + r;
+                        const f2 xl = pk2(xr0[0], xr0[Lp]), xh = pk2(xr0[1], xr0[Lp + 1]);
+                        const f2 kl = pk2(kr0[0], kr0[Lp]), kh = pk2(kr0[1], kr0[Lp + 1]);
+                        const f2 six = mul2(pk2(2.f, 2.f), mul2(pk2(3.f, 3.f), sub2(xh, xl)));
+                        const f2 sr = mul2(six, rdp);
+                        const f2 c2 = mul2(sub2(sub2(sr, mul2(pk2(4.f, 4.f), kl)), mul2(pk2(2.f, 2.f), kh)), rdp);   // :45-47
+                        const f2 d3 = mul2(sub2(mul2(pk2(3.f, 3.f), add2(kl, kh)), sr), rd2p);                          // :48-50
+                        upk2(xl, av[j], av[j + 1]);
+                        upk2(kl, bv[j], bv[j + 1]);
+                        upk2(c2, cv[j], cv[j + 1]);
+                        upk2(d3, dv[j], dv[j + 1]);
                     }
                     float4* row = ot4 + (size_t)i * (4 * Q) + q;
 #pragma unroll
