@@ -47,6 +47,10 @@ template <typename T> struct SolveArgs {
     int groups;              // path groups per CTA (TB = groups * ST)
     int threads;
     T sign;
+    // single evaluation mode (tcde_vector_field_linear): z0 is z, out[p][h] receives f(z) . dX/dt at
+    // (eval_index, eval_frac) and the kernel returns after the first stage; no schedule is read
+    int eval_only, eval_index;
+    T eval_frac;
 };
 
 // Shared-memory carve-up (all offsets in elements of T; every region 16-byte aligned):
@@ -193,7 +197,9 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
         }
     };
     int jn = 0;
-    while (jn < a.n_out && a.out_step[jn] < 0) { write_out(jn, y); ++jn; }
+    if (!a.eval_only) {
+        while (jn < a.n_out && a.out_step[jn] < 0) { write_out(jn, y); ++jn; }
+    }
 
     // stage 0 inputs
     if (worker) {
@@ -202,15 +208,15 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
 #pragma unroll
             for (int d = 0; d < ZD; ++d) zin[(size_t)h * TBp + (lp0 + s) * ZD + d] = y[s];
     }
-    fetch_rows(a.stage_index[0]);
-    produce_dx(a.stage_frac[0], dxs);
+    fetch_rows(a.eval_only ? a.eval_index : a.stage_index[0]);
+    produce_dx(a.eval_only ? a.eval_frac : a.stage_frac[0], dxs);
     __syncthreads();
 
     const int n_stages = a.n_stages;
-    const int total = a.n_steps * n_stages;
+    const int total = a.eval_only ? 1 : a.n_steps * n_stages;
     const T third = T(1.0 / 3.0);
     int step = 0, sub = 0;
-    T dt = a.step_dt[0];
+    T dt = a.eval_only ? T(0) : a.step_dt[0];
 
     for (int st = 0; st < total; ++st) {
         const int cur = st & 1, nxt = cur ^ 1;
@@ -320,6 +326,16 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
 #pragma unroll
                 for (int s = 0; s < ST; ++s) kv[s] = -kv[s];
             }
+        }
+        if (a.eval_only) {                       // out[p][h] = f(z) . dX/dt, nothing else
+            if (worker) {
+#pragma unroll
+                for (int s = 0; s < ST; ++s) {
+                    const int64_t p = path0 + lp0 + s;
+                    if (p < a.n_paths) a.out[p * H + h] = kv[s];
+                }
+            }
+            return;
         }
         // ---- Runge-Kutta combination (oracle/odeint_port.py, one rounding per op) ----------
         bool step_done = false;
@@ -530,6 +546,18 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
                         const void* z, void* out, int64_t n_paths, int C, int H, int index, double frac,
                         cudaStream_t stream) {
     TCDE_CHECK_SUPPORTED(H <= 256, "vector field: hidden=%d > 256", H);
+    {
+        // the register-tiled stage of the fused solve, run for exactly one evaluation
+        SolveArgs<T> a{};
+        a.control = (const T*)control; a.weight = (const T*)weight; a.bias = (const T*)bias;
+        a.z0 = (const T*)z; a.out = (T*)out;
+        a.n_paths = n_paths; a.n_rows = n_rows; a.C = C; a.H = H;
+        a.control_kind = control_kind; a.method = TCDE_EULER; a.n_stages = 1; a.n_steps = 1; a.n_out = 1;
+        a.sign = T(1);
+        a.eval_only = 1; a.eval_index = index; a.eval_frac = (T)frac;
+        const int rc = launch_solve<T, (sizeof(T) == 4 ? 8 : 4)>(a, false, stream);
+        if (rc != TCDE_ERR_UNSUPPORTED) return rc;
+    }
     const int ppc = 256 / H;
     const int threads = ppc * H;
     const size_t smem = (size_t)ppc * (H + C) * sizeof(T);
@@ -630,12 +658,12 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,
                            (float*)out, (const float*)step_dt, stage_index, (const float*)stage_frac, out_step,
                            out_mode, (const float*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
-                           control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (float)sign};
+                           control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (float)sign, 0, 0, 0.f};
         return solve_simt_f32(a, g_solve_variant == 4, s);   // FFMA2 path measured slower (34.6 vs 31.6 ms): opt-in only
     }
     SolveArgs<double> a{(const double*)control, (const double*)weight, (const double*)bias, (const double*)z0,
                         (double*)out, (const double*)step_dt, stage_index, (const double*)stage_frac, out_step,
                         out_mode, (const double*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
-                        control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (double)sign};
+                        control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (double)sign, 0, 0, 0.0};
     return solve_simt_f64(a, s);
 }
