@@ -318,3 +318,46 @@ def test_tensor_core_variant_full_size(variant):
         _assert_close(out[pick], want, torch.float32)
     finally:
         _set_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_decreasing_output_times(variant):
+    """A decreasing t is integrated as -t with the field negated (torchdiffeq's time reversal)."""
+    length, channels, hidden, batch = 20, 8, 32, 70
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(batch, length, channels, generator=gen, dtype=torch.float64).cumsum(1) / math.sqrt(length)
+    z0 = torch.randn(batch, hidden, generator=gen, dtype=torch.float64).float()
+    torch.manual_seed(9)
+    func = cde.LinearVectorField(hidden, channels).to(DEV)
+    co = O.hermite_backward_difference_coeffs(x).float()
+    X = cde.CubicSpline(co.to(DEV))
+    t_out = torch.tensor([length - 1.0, 12.5, 3.0, 0.0])
+    try:
+        _set_variant(variant)
+        with torch.no_grad():
+            out = cde.cdeint(X, func, z0.to(DEV), t_out, adjoint=False, method="rk4", options={"step_size": 0.5})
+            want = O.cdeint_linear(co.double(), O.knot_times(length, torch.float64),
+                                   func.linear.weight.detach().cpu().double(), func.linear.bias.detach().cpu().double(),
+                                   z0.double(), t_out.double(), "rk4", 0.5)
+        _assert_close(out, want, torch.float32)
+    finally:
+        _set_variant(0)
+
+
+def test_control_with_own_knots_on_device():
+    """Non-default knots live on the device: the schedule reads them back once (one sync), results as usual."""
+    length, channels, hidden, batch = 15, 8, 32, 33
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, length, channels, generator=gen, dtype=torch.float64).cumsum(1) / 4
+    knots = (torch.rand(length, generator=gen, dtype=torch.float64) + 0.3).cumsum(0)
+    z0 = torch.randn(batch, hidden, generator=gen, dtype=torch.float64)
+    torch.manual_seed(2)
+    func = cde.LinearVectorField(hidden, channels).to(DEV)
+    co = O.hermite_backward_difference_coeffs(x.float(), knots.float())
+    X = cde.CubicSpline(co.to(DEV), knots.float().to(DEV))
+    with torch.no_grad():
+        out = cde.cdeint(X, func, z0.float().to(DEV), X.interval, adjoint=False, method="rk4", options={"step_size": 0.25})
+        want = O.cdeint_linear(co.double(), knots.float().double(), func.linear.weight.detach().cpu().double(),
+                               func.linear.bias.detach().cpu().double(), z0.float().double(),
+                               torch.stack([knots.float()[0], knots.float()[-1]]).double(), "rk4", 0.25)
+    _assert_close(out, want, torch.float32)
