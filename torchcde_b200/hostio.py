@@ -65,42 +65,65 @@ def cdeint_from_host(control_host, func, z0_host, t, out_host=None, kind="cubic"
     return out_host
 
 
+class SeriesPipeline:
+    """Persistent streams and staging buffers for ``cdeint_from_host_series`` (reused across calls:
+    creating streams / device buffers per call would go through cudaMalloc every time)."""
+
+    def __init__(self, device, chunk_paths, length, channels, hidden, dtype):
+        self.device = torch.device(device)
+        self.chunk_paths = chunk_paths
+        self.key = (chunk_paths, length, channels, hidden, dtype)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+        self.x = [torch.empty(chunk_paths, length, channels, dtype=dtype, device=self.device) for _ in range(2)]
+        self.z0 = [torch.empty(chunk_paths, hidden, dtype=dtype, device=self.device) for _ in range(2)]
+        self.coeffs = [torch.empty(chunk_paths, length - 1, 4 * channels, dtype=dtype, device=self.device)
+                       for _ in range(2)]
+
+
+_series_pipelines = {}
+
+
 def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths=8192, device=None, **kwargs):
     """The whole user pipeline from raw series kept on the host: per chunk, copy ``x`` (pinned,
     (P, L, C)) in, build the Hermite backward-difference coefficients on the device
-    (``hermite_cubic_coefficients_with_backward_differences``), solve, copy the result out.  Moving
-    ``x`` instead of its coefficients cuts the PCIe traffic 4x; rebuilding the coefficients costs
-    ~0.5 ms per 65,536 paths on the device.  The series must be NaN-free (the NaN check of the public
-    builder needs a host read-back per chunk, which would serialise the pipeline); float32 / float64."""
+    (``hermite_cubic_coefficients_with_backward_differences``'s kernel), solve, copy the result out.
+    Moving ``x`` instead of its coefficients cuts the PCIe traffic 4x; rebuilding the coefficients
+    costs ~0.5 ms per 65,536 paths on the device.  The series must be NaN-free (the NaN check of the
+    public builder needs a host read-back per chunk, which would serialise the pipeline)."""
     device = torch.device(device if device is not None else "cuda")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     n_paths, hidden = z0_host.shape
+    length, channels = x_host.shape[1], x_host.shape[2]
     n_out = t.numel()
     if out_host is None:
         out_host = torch.empty(n_paths, n_out, hidden, dtype=z0_host.dtype, pin_memory=True)
     cp = min(chunk_paths, n_paths)
-    streams = [torch.cuda.Stream(device) for _ in range(2)]
-    xs = [torch.empty(cp, *x_host.shape[1:], dtype=x_host.dtype, device=device) for _ in range(2)]
-    zs = [torch.empty(cp, hidden, dtype=z0_host.dtype, device=device) for _ in range(2)]
+    key = (device.index, cp, length, channels, hidden, x_host.dtype)
+    pipe = _series_pipelines.get(key)
+    if pipe is None:
+        pipe = SeriesPipeline(device, cp, length, channels, hidden, x_host.dtype)
+        _series_pipelines.clear()              # keep one configuration's buffers alive, not every one ever seen
+        _series_pipelines[key] = pipe
     kwargs.setdefault("adjoint", False)
+    code = _lib.dtype_code(x_host.dtype)
     current = torch.cuda.current_stream(device)
-    for s in streams:
+    for s in pipe.streams:
         s.wait_stream(current)
     t_cpu = t.detach().cpu()
     with torch.no_grad():
         for i, lo in enumerate(range(0, n_paths, cp)):
             hi = min(lo + cp, n_paths)
             slot = i & 1
-            with torch.cuda.stream(streams[slot]):
-                x_dev = xs[slot][:hi - lo]
-                z_dev = zs[slot][:hi - lo]
+            with torch.cuda.stream(pipe.streams[slot]):
+                n = hi - lo
+                x_dev, z_dev, coeffs = pipe.x[slot][:n], pipe.z0[slot][:n], pipe.coeffs[slot][:n]
                 x_dev.copy_(x_host[lo:hi], non_blocking=True)
                 z_dev.copy_(z0_host[lo:hi], non_blocking=True)
-                n, length, channels = x_dev.shape
-                coeffs = torch.empty(n, length - 1, 4 * channels, dtype=x_dev.dtype, device=device)
                 _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(x_dev), None, _lib.ptr(coeffs), n, length, channels,
-                          _lib.dtype_code(x_dev.dtype), None, _lib.stream_of(x_dev))
+                          code, None, _lib.stream_of(x_dev))
                 out = cdeint(CubicSpline(coeffs), func, z_dev, t_cpu, **kwargs)
                 out_host[lo:hi].copy_(out, non_blocking=True)
-    for s in streams:
+    for s in pipe.streams:
         current.wait_stream(s)
     return out_host
