@@ -14,6 +14,16 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The C-ABI library is a build artefact (git-ignored).  In a fresh checkout build it before the
+    # first test needs it (nvcc cross-compiles for sm_100a without a GPU); never rebuild on the GPU box
+    # when the prebuilt library travelled with the snapshot.
+    lib = os.path.join(ROOT, "torchcde_b200", "csrc", "libtcde_b200.so")
+    if not os.path.isfile(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "torchcde_b200", "csrc"), "-j8"], check=False,
+                           capture_output=True)
 
 
 def pytest_collection_modifyitems(config, items):
