@@ -68,7 +68,9 @@ def synthetic(batch, device, seed):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in the background from the start of the run (its start-up takes longer than the
+    timed region); afterwards only the samples whose timestamps fall inside the timed window count."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -76,6 +78,7 @@ class ClockSampler:
         self.index = index
         self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.window = None
 
     def start(self):
         try:
@@ -84,6 +87,9 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def mark(self, t_begin, t_end):
+        self.window = (t_begin, t_end)
 
     def stop(self):
         if self.proc is None:
@@ -95,27 +101,35 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        sm, smax, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.file:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(parts[1]), float(parts[2]), [n for n, v in zip(names, parts[4:8]) if v == "Active"]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[4:8]):
-                if val == "Active":
-                    reasons.add(name)
         self.file.close()
         os.unlink(self.file.name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = sorted(sm)[len(sm) // 2:]                 # upper half = samples under load
-        return {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        picked, where = rows, "whole run"
+        if self.window is not None:
+            lo, hi = self.window
+            inside = [r for r in rows if lo - 0.02 <= r[0] <= hi + 0.02]
+            if inside:
+                picked, where = inside, "timed region"
+            else:
+                mid = 0.5 * (lo + hi)
+                picked, where = sorted(rows, key=lambda r: abs(r[0] - mid))[:3], "nearest to the timed region"
+        sm = sorted(r[1] for r in picked)
+        reasons = sorted({n for r in picked for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in picked), "reasons": reasons,
+                "samples": len(picked), "window": where}
 
 
 def time_loop(fn, steps, warmup, device, dist=None):
@@ -250,6 +264,9 @@ def run_gpu_arm(args):
     if args.variant is not None:
         _lib.call("tcde_set_solve_variant", args.variant)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     note("rank {} of {}: generating synthetic data".format(rank, world))
     x, z0, func = synthetic(BATCH, device, seed=1000 + rank)
     if dist is not None:
@@ -266,16 +283,14 @@ def run_gpu_arm(args):
             holder["out"] = cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options=options)
 
         note("timing {} solves".format(args.steps))
-        sampler = ClockSampler(local_rank)
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize(device)
+        wall_begin = time.time()
+        ms = time_loop(step, args.steps, 0, device, dist)
+        wall_end = time.time()
         if rank == 0:
-            sampler.start()
-            for _ in range(40):            # the timed region is only tens of ms: give nvidia-smi (20 ms period)
-                step()                     # the same kernel to look at for ~0.2 s around it
-        ms = time_loop(step, args.steps, args.warmup, device, dist)
-        if rank == 0:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize(device)
+            sampler.mark(wall_begin, wall_end)
         clocks = sampler.stop() if rank == 0 else None
         assert bool(torch.isfinite(holder["out"]).all())
 
