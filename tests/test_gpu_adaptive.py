@@ -101,6 +101,36 @@ def test_dopri5_linear_control_matches_exact_matrix_exponential():
     assert float((out[:, -1].cpu().double() - want).abs().max()) < 5e-4 * scale
 
 
+def test_dopri5_jump_t_on_linear_control():
+    """README.md:194-200: with a piecewise-linear control pass the knots as jump_t; same answer, far fewer steps."""
+    from torchcde_b200 import adaptive
+    x, z0, func = _problem(16, 12, 8, 32, seed=6)
+    func = func.to(DEV)
+    counts = []
+    real = adaptive.Dopri5.integrate
+
+    def counting(self, times):
+        out = real(self, times)
+        counts.append((self.n_accepted, self.n_rejected))
+        return out
+
+    adaptive.Dopri5.integrate = counting
+    try:
+        with torch.no_grad():
+            X = cde.LinearInterpolation(x.to(DEV))
+            plain = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8)
+            jumped = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8,
+                                options=dict(jump_t=X.grid_points))
+    finally:
+        adaptive.Dopri5.integrate = real
+    want = _exact_piecewise_linear(x.double(), func.linear.weight.detach().cpu().double(),
+                                   func.linear.bias.detach().cpu().double(), z0.double(), 11)
+    scale = float(want.abs().max())
+    assert float((jumped[:, -1].cpu().double() - want).abs().max()) < 5e-4 * scale
+    assert float((plain[:, -1].cpu().double() - want).abs().max()) < 5e-4 * scale
+    assert sum(counts[1]) < sum(counts[0])              # fewer attempted steps with jump_t
+
+
 def test_generic_func_shapes_like_reference_test_cdeint():
     """test_cdeint.py:6-46: sigmoid field, float64 output times with a float32 state, 0-2 batch dims."""
     gen = torch.Generator().manual_seed(11)

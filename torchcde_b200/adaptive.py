@@ -81,7 +81,7 @@ def _next_step(dt, ratio, safety=0.9, ifactor=10.0, dfactor=0.2):
 class Dopri5:
     """One adaptive solve of dy/dt = field(t, y) over increasing output times ``t`` (floats)."""
 
-    def __init__(self, field, y0, rtol, atol, first_step=None, max_num_steps=2 ** 31 - 1, norm=None):
+    def __init__(self, field, y0, rtol, atol, first_step=None, max_num_steps=2 ** 31 - 1, norm=None, jump_t=None):
         self.field, self.rtol, self.atol = field, float(rtol), float(atol)
         self.max_num_steps = max_num_steps
         self.norm = norm or _rms
@@ -89,6 +89,9 @@ class Dopri5:
         self.y0 = y0
         self.n_accepted = 0
         self.n_rejected = 0
+        # times at which the field is discontinuous (README.md:194-200, `options=dict(jump_t=X.grid_points)`):
+        # no step may straddle one, and the slope is re-evaluated just after it
+        self.jump_t = sorted(float(v) for v in jump_t) if jump_t is not None else []
 
     def _attempt(self, t0, dt, y0, f0):
         ks = [f0]
@@ -111,21 +114,29 @@ class Dopri5:
                                                                                self.atol)
         t_lo, t_hi = t0, t0
         coeff = None
+        jumps = [v for v in self.jump_t if v > t0]
         for target in times[1:]:
             tries = 0
             while target > t_hi:
                 if tries >= self.max_num_steps:
                     raise RuntimeError("max_num_steps exceeded ({}>={})".format(tries, self.max_num_steps))
-                y1, ks, ratio = self._attempt(t_hi, dt, y0, f0)
+                step = dt
+                on_jump = bool(jumps) and t_hi < jumps[0] < t_hi + dt
+                if on_jump:
+                    step = jumps[0] - t_hi
+                y1, ks, ratio = self._attempt(t_hi, step, y0, f0)
                 if ratio <= 1:
-                    y_mid = _combine(y0, ks, _C_MID, dt)
-                    coeff = self._fit(y0, y1, y_mid, ks[0], ks[-1], dt)
-                    t_lo, t_hi = t_hi, t_hi + dt
+                    y_mid = _combine(y0, ks, _C_MID, step)
+                    coeff = self._fit(y0, y1, y_mid, ks[0], ks[-1], step)
+                    t_lo, t_hi = t_hi, (jumps[0] if on_jump else t_hi + step)
                     y0, f0 = y1, ks[-1]
+                    if on_jump:
+                        jumps.pop(0)
+                        f0 = self.field(t_hi, y0, 1)      # the slope just AFTER the discontinuity
                     self.n_accepted += 1
                 else:
                     self.n_rejected += 1
-                dt = _next_step(dt, ratio)
+                dt = _next_step(step, ratio)
                 tries += 1
             out.append(self._evaluate(coeff, t_lo, t_hi, target))
         return torch.stack(out, dim=0)
@@ -151,8 +162,11 @@ class Dopri5:
 def odeint_dopri5(field, y0, times, rtol, atol, options=None):
     """``times``: increasing Python floats.  Returns (len(times), *y0.shape)."""
     options = dict(options or {})
+    jump_t = options.pop("jump_t", None)
+    if isinstance(jump_t, torch.Tensor):
+        jump_t = jump_t.detach().cpu().tolist()
     solver = Dopri5(field, y0, rtol, atol, first_step=options.pop("first_step", None),
-                    max_num_steps=options.pop("max_num_steps", 2 ** 31 - 1))
+                    max_num_steps=options.pop("max_num_steps", 2 ** 31 - 1), jump_t=jump_t)
     if options:
         raise NotImplementedError("dopri5: unsupported options {}".format(sorted(options)))
     out = solver.integrate(list(times))

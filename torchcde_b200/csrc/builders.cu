@@ -600,13 +600,6 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
         }
         __syncthreads();
         if (L > 2) {
-            // scaled differences sc[i] = 3 (x[i+1] - x[i]) / dt_i^2 (0 for the last knot), parked in ks
-            for (int e = tid; e < C * L; e += kThreads) {
-                const int c = e / L, i = e - c * L;
-                const T* xr = xs + c * Lp + i;
-                ks[c * Lp + i] = (i < L - 1) ? E::mul(E::mul(T(3), E::sub(xr[1], xr[0])), rdt2[i]) : T(0);
-            }
-            __syncthreads();
             const bool pairs = (sizeof(T) == 4) && ((C & 1) == 0);
             if (pairs) {
                 // two series per thread, packed arithmetic: half the instructions of the scalar sweeps
@@ -615,13 +608,24 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
                 for (int it = tid; it < n_pair_items; it += kThreads) {     // forward sweep (misc.py:58-61)
                     const int c = 2 * (it % C2), j = it / C2;
                     const int g0 = j * G, g1 = min(g0 + G, L);
-                    const float* s0 = reinterpret_cast<const float*>(ks) + c * Lp;
+                    const float* x0 = reinterpret_cast<const float*>(xs) + c * Lp;
                     float* f0 = reinterpret_cast<float*>(fs) + c * Lp;
                     int i = max(g0 - wf, 0);
                     f2 f = pk2(0.f, 0.f);
-                    f2 sc_prev = (i > 0) ? pk2(s0[i - 1], s0[Lp + i - 1]) : pk2(0.f, 0.f);
+                    const f2 three = pk2(3.f, 3.f);
+                    f2 x_lo = pk2(x0[i], x0[Lp + i]);
+                    f2 sc_prev = pk2(0.f, 0.f);
+                    if (i > 0) {
+                        const float r2 = (float)rdt2[i - 1];
+                        sc_prev = mul2(mul2(three, sub2(x_lo, pk2(x0[i - 1], x0[Lp + i - 1]))), pk2(r2, r2));
+                    }
                     for (; i < g1; ++i) {
-                        const f2 sc = pk2(s0[i], s0[Lp + i]);
+                        // scaled difference 3 (x[i+1] - x[i]) / dt_i^2; rdt2[L-1] = 0 closes the system (cubic.py:36-39)
+                        const int in = min(i + 1, L - 1);
+                        const f2 x_hi = pk2(x0[in], x0[Lp + in]);
+                        const float r2 = (float)rdt2[i];
+                        const f2 sc = mul2(mul2(three, sub2(x_hi, x_lo)), pk2(r2, r2));
+                        x_lo = x_hi;
                         const float m = (float)mult[i];
                         f = sub2(add2(sc, sc_prev), mul2(pk2(m, m), f));
                         sc_prev = sc;
@@ -632,13 +636,16 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
                 for (int it = tid; it < n_items; it += kThreads) {
                     const int c = it % C, j = it / C;
                     const int g0 = j * G, g1 = min(g0 + G, L);
-                    const T* sr = ks + c * Lp;
+                    const T* xr = xs + c * Lp;
                     T* fr = fs + c * Lp;
                     int i = max(g0 - wf, 0);
                     T f = T(0);
-                    T sc_prev = (i > 0) ? sr[i - 1] : T(0);
+                    T x_lo = xr[i];
+                    T sc_prev = (i > 0) ? E::mul(E::mul(T(3), E::sub(x_lo, xr[i - 1])), rdt2[i - 1]) : T(0);
                     for (; i < g1; ++i) {
-                        const T sc = sr[i];
+                        const T x_hi = xr[min(i + 1, L - 1)];
+                        const T sc = E::mul(E::mul(T(3), E::sub(x_hi, x_lo)), rdt2[i]);      // rdt2[L-1] = 0
+                        x_lo = x_hi;
                         f = E::sub(E::add(sc, sc_prev), E::mul(mult[i], f));     // cubic.py:36-39, misc.py:61
                         sc_prev = sc;
                         if (i >= g0) fr[i] = f;
@@ -1119,6 +1126,12 @@ static int launch_natural(const T* x, const T* t, T* out, T* ws, int64_t n_paths
         const int Lpw = ((L + 31) / 32) * 32 + 1;
         int G = (int)(((int64_t)L * C + kThreads - 1) / kThreads);
         if (G < 4) G = 4;
+        // coefficient tiles: at least one (interval, 4-channel) item per thread and tile (a tile costs two
+        // CTA barriers and a bulk store), at most 16 KB per staging buffer
+        int TRw = TR;
+        while (TRw < L - 1 && (size_t)TRw * (C / 4 > 0 ? C / 4 : 1) < (size_t)kThreads && (size_t)(2 * TRw) * row_bytes <= 16384) TRw *= 2;
+        if (TRw > L - 1) TRw = L - 1;
+        const int TR = TRw;
         const size_t smem_w = 2 * TR * row_bytes + (size_t)(4 * L + 8) * sizeof(T) + (size_t)3 * C * Lpw * sizeof(T) + 16;
         if (smem_w <= 64 * 1024 && g_natural_variant != 1) {
             auto kw = natural_win_kernel<T>;

@@ -438,6 +438,10 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
         times = [-v for v in times]
     if any(b <= a for a, b in zip(times[:-1], times[1:])):
         raise ValueError("t must be strictly increasing or decreasing")
+    if method == "dopri5" and options.get("jump_t", None) is not None:
+        jumps = options["jump_t"]
+        jumps = jumps.detach().cpu().tolist() if isinstance(jumps, torch.Tensor) else list(jumps)
+        options["jump_t"] = sorted(-float(v) for v in jumps) if flipped else sorted(float(v) for v in jumps)
 
     def fast_field():
         f = _kernel_field(X, field_params[0], field_params[1], z0) if field_params is not None \
