@@ -683,6 +683,44 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
             }
         }
         __syncthreads();
+        if (vec4) {
+            // coefficient rows straight from registers to global memory: thread = (interval, 4 channels), four
+            // 128-bit stores that each fill whole 32-byte sectors (a warp completes its 128-byte lines across
+            // the four instructions).  No staging tile: the shared memory saved doubles the resident CTAs.
+            const int Q = C >> 2;
+            float4* og4 = reinterpret_cast<float4*>(out + p * (int64_t)(L - 1) * row_elems);
+            int i = tid / Q, q = tid - (tid / Q) * Q;
+            const int dq_i = kThreads / Q, dq_q = kThreads - dq_i * Q;
+            for (int e = tid; e < (L - 1) * Q; e += kThreads) {
+                const float rd = (float)rdt[i], rd2 = (float)rdt2[i];
+                const f2 rdp = pk2(rd, rd), rd2p = pk2(rd2, rd2);
+                float av[4], bv[4], cv[4], dv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const float* xr0 = reinterpret_cast<const float*>(xs) + (4 * q + j) * Lp + i;
+                    const float* kr0 = reinterpret_cast<const float*>(ks) + (4 * q + j) * Lp + i;
+                    const f2 xl = pk2(xr0[0], xr0[Lp]), xh = pk2(xr0[1], xr0[Lp + 1]);
+                    const f2 kl = pk2(kr0[0], kr0[Lp]), kh = pk2(kr0[1], kr0[Lp + 1]);
+                    const f2 six = mul2(pk2(2.f, 2.f), mul2(pk2(3.f, 3.f), sub2(xh, xl)));
+                    const f2 sr = mul2(six, rdp);
+                    const f2 c2 = mul2(sub2(sub2(sr, mul2(pk2(4.f, 4.f), kl)), mul2(pk2(2.f, 2.f), kh)), rdp);   // :45-47
+                    const f2 d3 = mul2(sub2(mul2(pk2(3.f, 3.f), add2(kl, kh)), sr), rd2p);                          // :48-50
+                    upk2(xl, av[j], av[j + 1]);
+                    upk2(kl, bv[j], bv[j + 1]);
+                    upk2(c2, cv[j], cv[j + 1]);
+                    upk2(d3, dv[j], dv[j + 1]);
+                }
+                float4* row = og4 + (size_t)i * (4 * Q) + q;
+                row[0] = make_float4(av[0], av[1], av[2], av[3]);
+                row[Q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                row[2 * Q] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                row[3 * Q] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+            continue;
+        }
         for (int r0 = 0; r0 < L - 1; r0 += TR, buf ^= 1) {
             const int nr = min(TR, L - 1 - r0);
             if (use_bulk && tid == 0) bulk_wait_read<1>();
@@ -1131,7 +1169,8 @@ static int launch_natural(const T* x, const T* t, T* out, T* ws, int64_t n_paths
         int TRw = TR;
         while (TRw < L - 1 && (size_t)TRw * (C / 4 > 0 ? C / 4 : 1) < (size_t)kThreads && (size_t)(2 * TRw) * row_bytes <= 16384) TRw *= 2;
         if (TRw > L - 1) TRw = L - 1;
-        const int TR = TRw;
+        const bool direct = (sizeof(T) == 4) && ((C & 3) == 0) && L > 2 && aligned16(out) && aligned16(x);
+        const int TR = direct ? 1 : TRw;      // the vectorised path stores rows straight to global memory
         const size_t smem_w = 2 * TR * row_bytes + (size_t)(4 * L + 8) * sizeof(T) + (size_t)3 * C * Lpw * sizeof(T) + 16;
         if (smem_w <= 64 * 1024 && g_natural_variant != 1) {
             auto kw = natural_win_kernel<T>;
