@@ -372,7 +372,7 @@ def run_gpu_arm(args):
     fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
     variant = args.variant if args.variant is not None else 0
-    tensor_kernel = variant in (0, 2, 3)
+    tensor_kernel = variant in (0, 2)
     mma_flops = BATCH * 255 * 4 * 3 * 2 * HIDDEN * HIDDEN * CHANNELS      # 3xTF32: three MMAs per product
     line = {
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
@@ -430,7 +430,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", type=int, default=None, help="solve kernel: 1 = CUDA-core, 2 = tcgen05 (default: library's choice)")
+    ap.add_argument("--variant", type=int, default=None, help="solve kernel: 1 = CUDA-core, 2 = tcgen05 (default: the library's choice)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

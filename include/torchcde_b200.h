@@ -158,10 +158,10 @@ TCDE_API int tcde_set_trace_buffer(void* device_buffer);
  * when the path fits shared memory (default), 1 = one thread per series.  For tests / benchmarks. */
 TCDE_API int tcde_set_natural_variant(int variant);
 
-/* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic choice,
- * 1 = CUDA-core kernel (any shape), 2 / 3 = tcgen05 tensor-core kernel, one / two row threads per
- * path (hidden = 32, channels = 8; TCDE_ERR_UNSUPPORTED otherwise).  Process-wide; meant for tests
- * and benchmarks. */
+/* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic (the tcgen05 kernel
+ * where it is built for the shape: hidden = 32, channels = 8; the CUDA-core kernel otherwise),
+ * 1 = CUDA-core kernel, 2 = tcgen05 kernel (TCDE_ERR_UNSUPPORTED for other shapes).
+ * Process-wide; meant for tests and benchmarks. */
 TCDE_API int tcde_set_solve_variant(int variant);
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ t = torch.tensor([0.0, L - 1.0])
 trace = torch.zeros(64, 8, dtype=torch.int64, device=dev)
 with torch.no_grad():
     X = cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x))
-    for variant in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,5").split(",")]:
+    for variant in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2").split(",")]:
         _lib.call("tcde_set_solve_variant", variant)
         cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options={"step_size": 1.0})
         trace.zero_()

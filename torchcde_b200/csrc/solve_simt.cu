@@ -21,12 +21,6 @@ namespace tcde {
 
 template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
 
-// packed fp32x2 FMA (sm_100 FFMA2): two IEEE fp32 fused multiply-adds per instruction issue
-typedef uint64_t f2;
-__device__ __forceinline__ f2 pk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f2 fma2p(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-
 template <typename T> struct SolveArgs {
     const T* control;        // cubic: [P][n_rows][4C]   linear: slopes [P][n_rows][C]
     const T* weight;         // [H*C][H]
@@ -66,10 +60,10 @@ template <typename T> struct SolveSmem {
     int TB, TBp;
 };
 
-template <typename T> static SolveSmem<T> solve_smem_layout(int H, int Cp, int groups, int ST, int threads, int zdup) {
+template <typename T> static SolveSmem<T> solve_smem_layout(int H, int Cp, int groups, int ST, int threads) {
     SolveSmem<T> s;
     s.TB = groups * ST;
-    s.TBp = s.TB * zdup + 4;       // zdup = 2: every z stored twice so that a 64-bit load yields the {z, z} operand of FFMA2
+    s.TBp = s.TB + 4;
     size_t off = 0;
     s.ws = off; off += (size_t)H * Cp * H;
     s.bs = off; off += (size_t)Cp * H;
@@ -81,11 +75,9 @@ template <typename T> static SolveSmem<T> solve_smem_layout(int H, int Cp, int g
     return s;
 }
 
-template <typename T, int ST, int CT, bool PACK>
+template <typename T, int ST, int CT>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 && ST * CT >= 64) ? 2 : 1)
 cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
-    static_assert(!PACK || (sizeof(T) == 4 && CT == 8 && ST == 8), "packed path: float, 8 x 8 register tile");
-    constexpr int ZD = PACK ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using E = exact<T>;
     using P4 = Pack<T, 4>;
@@ -204,9 +196,7 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
     // stage 0 inputs
     if (worker) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s)
-#pragma unroll
-            for (int d = 0; d < ZD; ++d) zin[(size_t)h * TBp + (lp0 + s) * ZD + d] = y[s];
+        for (int s = 0; s < ST; ++s) zin[(size_t)h * TBp + lp0 + s] = y[s];
     }
     fetch_rows(a.eval_only ? a.eval_index : a.stage_index[0]);
     produce_dx(a.eval_only ? a.eval_frac : a.stage_frac[0], dxs);
@@ -231,57 +221,11 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
 #pragma unroll
         for (int s = 0; s < ST; ++s) kv[s] = T(0);
         if (worker) {
-            const T* zc = zin + (size_t)cur * H * TBp + lp0 * ZD;
+            const T* zc = zin + (size_t)cur * H * TBp + lp0;
             const T* dc = dxs + (size_t)cur * TB * Cp + (size_t)lp0 * Cp;
             for (int q0 = 0; q0 < nq; q0 += CT / 4) {
                 const T* wk = Ws + ((size_t)q0 * H + h) * 4;
-                if constexpr (PACK) {
-                    // 8 paths x 4 channel pairs of FFMA2 accumulators; operands arrive as 64-bit pairs:
-                    // {z, z} from the duplicated z tile, {w[c], w[c+1]} straight from W^T
-                    f2 acc2[ST][CT / 2];
-#pragma unroll
-                    for (int cc = 0; cc < CT / 4; ++cc) {
-                        const P4 b4 = *reinterpret_cast<const P4*>(bs + ((size_t)(q0 + cc) * H + h) * 4);
-#pragma unroll
-                        for (int s = 0; s < ST; ++s) {
-                            acc2[s][2 * cc] = pk2(b4.v[0], b4.v[1]);
-                            acc2[s][2 * cc + 1] = pk2(b4.v[2], b4.v[3]);
-                        }
-                    }
-#pragma unroll 2
-                    for (int k = 0; k < H; ++k) {
-                        f2 zz[ST], ww[CT / 2];
-#pragma unroll
-                        for (int s2 = 0; s2 < ST / 2; ++s2) {
-                            const ulonglong2 z2 = *reinterpret_cast<const ulonglong2*>(zc + (size_t)k * TBp + 4 * s2);
-                            zz[2 * s2] = z2.x;
-                            zz[2 * s2 + 1] = z2.y;
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < CT / 4; ++cc) {
-                            const ulonglong2 w2 = *reinterpret_cast<const ulonglong2*>(wk + (size_t)k * Cp * H + (size_t)cc * H * 4);
-                            ww[2 * cc] = w2.x;
-                            ww[2 * cc + 1] = w2.y;
-                        }
-#pragma unroll
-                        for (int s = 0; s < ST; ++s)
-#pragma unroll
-                            for (int c2 = 0; c2 < CT / 2; ++c2) acc2[s][c2] = fma2p(zz[s], ww[c2], acc2[s][c2]);
-                    }
-#pragma unroll
-                    for (int s = 0; s < ST; ++s) {
-                        f2 part = pk2(0.f, 0.f);
-#pragma unroll
-                        for (int cc = 0; cc < CT / 4; ++cc) {
-                            const ulonglong2 d2 = *reinterpret_cast<const ulonglong2*>(dc + (size_t)s * Cp + 4 * (q0 + cc));
-                            part = fma2p(acc2[s][2 * cc], d2.x, part);
-                            part = fma2p(acc2[s][2 * cc + 1], d2.y, part);
-                        }
-                        float lo, hi;
-                        upk2(part, lo, hi);
-                        kv[s] += lo + hi;
-                    }
-                } else {
+                {
                     T acc[ST][CT];
 #pragma unroll
                     for (int cc = 0; cc < CT / 4; ++cc) {
@@ -410,22 +354,13 @@ cdeint_simt_kernel(const SolveArgs<T> a, const SolveSmem<T> lay) {
         }
         if (more) {
             if (worker) {
-                T* zo = zin + (size_t)nxt * H * TBp + (size_t)h * TBp + lp0 * ZD;
-                if constexpr (PACK) {
+                T* zo = zin + (size_t)nxt * H * TBp + (size_t)h * TBp + lp0;
 #pragma unroll
-                    for (int s2 = 0; s2 < ST / 2; ++s2) {
-                        P4 o;
-                        o.v[0] = zn[2 * s2]; o.v[1] = zn[2 * s2]; o.v[2] = zn[2 * s2 + 1]; o.v[3] = zn[2 * s2 + 1];
-                        *reinterpret_cast<P4*>(zo + 4 * s2) = o;
-                    }
-                } else {
+                for (int s4 = 0; s4 < ST / 4; ++s4) {
+                    P4 o;
 #pragma unroll
-                    for (int s4 = 0; s4 < ST / 4; ++s4) {
-                        P4 o;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o.v[j] = zn[4 * s4 + j];
-                        *reinterpret_cast<P4*>(zo + 4 * s4) = o;
-                    }
+                    for (int j = 0; j < 4; ++j) o.v[j] = zn[4 * s4 + j];
+                    *reinterpret_cast<P4*>(zo + 4 * s4) = o;
                 }
             }
             produce_dx(next_frac, dxs + (size_t)nxt * TB * Cp);
@@ -478,9 +413,9 @@ vector_field_kernel(const T* __restrict__ control, int control_kind, int64_t n_r
     out[p * H + h] = res;
 }
 
-template <typename T, int ST, int CT, bool PACK>
+template <typename T, int ST, int CT>
 static int launch_solve_ct(SolveArgs<T> a, cudaStream_t stream) {
-    auto kern = cdeint_simt_kernel<T, ST, CT, PACK>;
+    auto kern = cdeint_simt_kernel<T, ST, CT>;
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int g_max = 256 / a.H;
     if (g_max < 1) g_max = 1;
@@ -496,7 +431,7 @@ static int launch_solve_ct(SolveArgs<T> a, cudaStream_t stream) {
     SolveSmem<T> best_lay{};
     for (int g = g_max; g >= (g_max + 1) / 2; --g) {
         const int threads = ((g * a.H + 31) / 32) * 32;
-        SolveSmem<T> lay = solve_smem_layout<T>(a.H, a.Cp, g, ST, threads, PACK ? 2 : 1);
+        SolveSmem<T> lay = solve_smem_layout<T>(a.H, a.Cp, g, ST, threads);
         if (lay.total > 220 * 1024) continue;
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, lay.total) != cudaSuccess || occ < 1)
@@ -525,21 +460,16 @@ static int launch_solve_ct(SolveArgs<T> a, cudaStream_t stream) {
 }
 
 template <typename T, int ST>
-static int launch_solve(const SolveArgs<T>& a_in, bool packed, cudaStream_t stream) {
+static int launch_solve(const SolveArgs<T>& a_in, cudaStream_t stream) {
     SolveArgs<T> a = a_in;
     TCDE_CHECK_SUPPORTED(a.H <= 256, "fused solve: hidden=%d > 256 is not supported by the CUDA-core kernel", a.H);
     a.Cp = ((a.C + 3) / 4) * 4;
-    if (a.Cp % 8 == 0) {
-        if constexpr (sizeof(T) == 4 && ST == 8) {
-            if (packed) return launch_solve_ct<T, ST, 8, true>(a, stream);
-        }
-        return launch_solve_ct<T, ST, 8, false>(a, stream);
-    }
-    return launch_solve_ct<T, ST, 4, false>(a, stream);
+    if (a.Cp % 8 == 0) return launch_solve_ct<T, ST, 8>(a, stream);
+    return launch_solve_ct<T, ST, 4>(a, stream);
 }
 
-int solve_simt_f32(const SolveArgs<float>& a, bool packed, cudaStream_t s) { return launch_solve<float, 8>(a, packed, s); }
-int solve_simt_f64(const SolveArgs<double>& a, cudaStream_t s) { return launch_solve<double, 4>(a, false, s); }
+int solve_simt_f32(const SolveArgs<float>& a, cudaStream_t s) { return launch_solve<float, 8>(a, s); }
+int solve_simt_f64(const SolveArgs<double>& a, cudaStream_t s) { return launch_solve<double, 4>(a, s); }
 
 template <typename T>
 static int launch_field(const void* control, int control_kind, int64_t n_rows, const void* weight, const void* bias,
@@ -555,7 +485,7 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
         a.control_kind = control_kind; a.method = TCDE_EULER; a.n_stages = 1; a.n_steps = 1; a.n_out = 1;
         a.sign = T(1);
         a.eval_only = 1; a.eval_index = index; a.eval_frac = (T)frac;
-        const int rc = launch_solve<T, (sizeof(T) == 4 ? 8 : 4)>(a, false, stream);
+        const int rc = launch_solve<T, (sizeof(T) == 4 ? 8 : 4)>(a, stream);
         if (rc != TCDE_ERR_UNSUPPORTED) return rc;
     }
     const int ppc = 256 / H;
@@ -578,14 +508,13 @@ struct UmmaArgs {
     int64_t n_paths; int64_t n_rows;
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
-    int split_terms;
     long long* trace;
 };
 bool solve_umma_supported(int H, int C);
-int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t stream);
+int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
 
 static long long* g_trace = nullptr;   // profiling aid: device buffer for in-kernel clock stamps (see tcde_set_trace_buffer)
-static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core scalar FFMA, 2 / 3 tensor-core v1 / v2, 4 CUDA-core FFMA2
+static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
 
 }  // namespace tcde
 
@@ -597,10 +526,7 @@ extern "C" int tcde_set_trace_buffer(void* device_buffer) {
 }
 
 extern "C" int tcde_set_solve_variant(int variant) {
-    TCDE_CHECK_ARG(variant >= 0 && variant <= 6,
-                   "variant=%d (0 auto, 1 cuda-core scalar FFMA, 2 tensor-core v1, 3 tensor-core v2, 4 cuda-core FFMA2, "
-                   "5 / 6 = timing experiments: v1 / v2 with a single TF32 term, WRONG results)",
-                   variant);
+    TCDE_CHECK_ARG(variant >= 0 && variant <= 2, "variant=%d (0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel)", variant);
     g_solve_variant = variant;
     return TCDE_OK;
 }
@@ -647,19 +573,19 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
         const bool umma_ok = solve_umma_supported((int)hidden, (int)channels) &&
                              ((reinterpret_cast<uintptr_t>(control) | reinterpret_cast<uintptr_t>(z0) |
                                reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-        const bool want_umma = (g_solve_variant == 2 || g_solve_variant == 3 || g_solve_variant >= 5) || (g_solve_variant == 0 && umma_ok);
+        const bool want_umma = (g_solve_variant == 2) || (g_solve_variant == 0 && umma_ok);
         if (want_umma) {
             UmmaArgs u{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0, (float*)out,
                        (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
-                       (int)n_out, (float)sign, (g_solve_variant == 5 || g_solve_variant == 6) ? 1 : 3, g_trace};
-            return solve_umma_f32(u, (int)hidden, (int)channels, (g_solve_variant == 3 || g_solve_variant == 6) ? 2 : 1, s);
+                       (int)n_out, (float)sign, g_trace};
+            return solve_umma_f32(u, (int)hidden, (int)channels, s);
         }
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,
                            (float*)out, (const float*)step_dt, stage_index, (const float*)stage_frac, out_step,
                            out_mode, (const float*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
                            control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (float)sign, 0, 0, 0.f};
-        return solve_simt_f32(a, g_solve_variant == 4, s);   // FFMA2 path measured slower (34.6 vs 31.6 ms): opt-in only
+        return solve_simt_f32(a, s);
     }
     SolveArgs<double> a{(const double*)control, (const double*)weight, (const double*)bias, (const double*)z0,
                         (double*)out, (const double*)step_dt, stage_index, (const double*)stage_frac, out_step,

@@ -13,15 +13,19 @@
 // CTA anatomy (288 threads, one CTA per SM, all 512 TMEM columns):
 //   * two independent tiles of 128 paths; tile T owns TMEM columns [256T, 256T+256);
 //   * warps 0-3 / 4-7: the 128 "row" threads of tile 0 / 1 -- thread r owns path r of its tile:
-//     its hidden state y[32] lives in registers for all steps; per stage it reads its 256
-//     accumulators from TMEM (tcgen05.ld), adds the bias, contracts with its own dX/dt (8
-//     values from the spline row it prefetched with cp.async), does the Runge-Kutta
-//     combination in the reference's operation order, splits the next stage input into
-//     hi / lo and writes both into the K-major 128B-swizzled A tiles in shared memory;
-//   * warp 8: allocates TMEM, then only issues: wait "A ready" -> 12 x tcgen05.mma ->
-//     tcgen05.commit -> "D ready".  While tile 0's MMAs run, tile 1's rows do their epilogue
-//     and vice versa, so the tensor pipe and the FP32 pipe overlap.
+//     its hidden state y[32] lives in registers for all steps; per stage it forms its own dX/dt (8
+//     values from the spline row it prefetched with cp.async one stage ahead), reads its 256
+//     accumulators from TMEM (tcgen05.ld, next load in flight), contracts them with dX/dt (packed
+//     FFMA2), does the Runge-Kutta combination in the reference's operation order (packed
+//     FADD2/FMUL2, parked slopes in shared memory), splits the next stage input into hi / lo and
+//     writes both into the K-major 128B-swizzled A tiles in shared memory;
+//   * warp 8: allocates TMEM, then only issues: wait "A ready" -> 13 x tcgen05.mma (12 for the
+//     3xTF32 split, 1 that adds the bias through a K-augmentation tile) -> tcgen05.commit ->
+//     "D ready".  While tile 0's MMAs run, tile 1's rows do their epilogue and vice versa.
 //   W^T (hi and lo, 64 KB) stays resident in shared memory for the whole solve.
+// Measured chain of one tile-stage (scripts/trace_umma.py, profiles/r01_umma_trace.txt):
+// MMAs 1331 cycles -> visible to the rows +525 -> contraction 669 -> Runge-Kutta 890 -> split, store,
+// fence, arrive 551 -> issuer wakes +97; the tensor pipe is busy 72 % of the time.
 #include "common.cuh"
 
 namespace tcde {
@@ -42,7 +46,6 @@ struct UmmaArgs {
     int64_t n_rows;
     int control_kind, method, n_stages, n_steps, n_out;
     float sign;
-    int split_terms;     // 3 = 3xTF32 (the product); 1 = hi.hi only -- a TIMING EXPERIMENT for profiling, never dispatched by default
     long long* trace;    // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
 };
 
@@ -99,24 +102,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 lanes x 32 columns: thread i of the warp receives columns [col, col+32) of TMEM lane (base lane + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // K-major, 128-byte-swizzled operand tile: row r (M or N index) is the 128 bytes at r*128; its
 // 16-byte chunk c lives at chunk position c ^ (r & 7).  Descriptor fields (cute mma_sm100_desc.hpp):
 // start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups,
@@ -144,31 +129,9 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
 
-// 32 lanes x 32 columns, issue and wait separated so that the next load overlaps the arithmetic on
-// the current one.  The destination registers go through the wait statement ("+r") so that the
-// compiler cannot schedule a use above it.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-
+// 32 lanes x 16 columns, issue and wait separated so that the next load overlaps the arithmetic on the
+// current one.  The destination registers go through the wait statement ("+r") so that the compiler
+// cannot schedule a use above it.
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -285,17 +248,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
                     const uint32_t d = tmem_base + (uint32_t)(t * N);
                     // small terms first; each k-block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
-                    if (a.split_terms == 3) {
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
-                    } else {
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
-                    }
+                    for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
                     mma_tf32(d, da_aug, db_aug, idesc, 1);                // + bias (1 * bias_hi + 1 * bias_lo)
                     mma_commit(&d_ready[t]);
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
@@ -538,387 +496,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
     if (warp == kTiles * 4) tmem_dealloc(tmem_base, 512);
 }
 
-// =================================================================================================
-// Version 2: two row threads per path, nothing but registers on the post-MMA critical path.
-//
-// In-kernel clock stamps of version 1 (scripts/trace_umma.py, profiles/r01_umma_trace.txt) show
-// that a tile's stage is a serial chain -- 12 MMAs issued+executed (~1250 cycles), completion
-// visible to the rows (~500), contraction (~1330), Runge-Kutta combination (~1130, dominated by
-// shared-memory round trips of the parked slopes), hi/lo split + store + fence + arrive (~720),
-// wake-up of the issuer (~280) -- so the tensor pipe idles half of the time and the chain, not
-// the MMA count, sets the pace.  This version shortens the chain:
-//   * every path gets TWO threads, each owning 16 of the 32 hidden units (128 accumulator columns);
-//   * k1 and k2(+k3) stay in registers (no shared-memory parking);
-//   * everything that does not depend on the MMA result runs BEFORE the wait, in the MMA's shadow:
-//     the spline row is loaded (read-only 128-bit loads), dX/dt is formed, and the bias part of
-//     the contraction  sum_c bias[h,c] dX[c]  is computed;
-//   * after the wait only  sum_c D[h,c] dX[c]  remains: packed FFMA2 on 16-column TMEM loads that
-//     are issued one ahead, then the packed Runge-Kutta combination, the TF32 split and the store.
-namespace v2 {
-
-constexpr int kHalf = kH / 2;                       // hidden units per thread
-constexpr int kThreads2 = kTiles * kTile * 2 + 32;  // 544
-
-// 32 lanes x 8 columns (= the 8 channels of one hidden unit)
-__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-// Wait for this thread's outstanding tcgen05.ld.  The destination registers are passed through the
-// statement ("+r") so that the compiler cannot schedule any use of them above the wait.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-                 :
-                 : "memory");
-}
-
-template <int N> struct Smem2 {
-    static constexpr int b_hi = 0;
-    static constexpr int b_lo = b_hi + N * 128;
-    static constexpr int a_hi = b_lo + N * 128;                          // [kTiles][128 rows][128 B]
-    static constexpr int a_lo = a_hi + kTiles * kTile * 128;
-    static constexpr int bias = a_lo + kTiles * kTile * 128;             // [N] floats
-    static constexpr int park = bias + N * 4;                            // [2 (y, k1)][kTiles][kH][kTile] floats
-    // bias as a 13th MMA: A_aug[128][8] = (1, 1, 0, ...) and B_aug[N][8] = (bias_hi, bias_lo, 0, ...),
-    // K-major WITHOUT swizzle: 8-row x 16-byte core matrices, k 4..7 at +128 B, next 8 rows at +256 B
-    static constexpr int a_aug = park + 2 * kTiles * kH * kTile * 4;     // 128 rows x 32 B
-    static constexpr int b_aug = a_aug + kTile * 32;                     // N rows x 32 B
-    static constexpr int bars = b_aug + N * 32;
-    static constexpr int total = bars + 64;
-};
-
-template <int C, bool TRACE>
-__global__ void __launch_bounds__(kThreads2, 1) cdeint_umma2_kernel(const UmmaArgs a) {
-    constexpr int N = kH * C;
-    static_assert(C == 8 && N == 256, "written for 8 channels x 32 hidden units");
-    using S = Smem2<N>;
-    using E = exact<float>;
-    extern __shared__ unsigned char smem_unaligned[];
-    unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
-    float* b_hi = reinterpret_cast<float*>(smem + S::b_hi);
-    float* b_lo = reinterpret_cast<float*>(smem + S::b_lo);
-    float* bias_s = reinterpret_cast<float*>(smem + S::bias);
-    uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
-    uint64_t* d_ready = a_ready + kTiles;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int64_t cta_path0 = (int64_t)blockIdx.x * (kTile * kTiles);
-    const int total = a.n_steps * a.n_stages;
-    constexpr int kMmaWarp = kTiles * 8;
-
-    for (int e = tid; e < N * kH; e += kThreads2) {
-        const int n = e >> 5, k = e & 31;
-        const float w = a.weight[e];
-        const float hi = tf32_hi(w);
-        b_hi[swz(n, k)] = hi;
-        b_lo[swz(n, k)] = w - hi;
-    }
-    for (int e = tid; e < N; e += kThreads2) bias_s[e] = a.bias[e];
-    {
-        float* a_aug = reinterpret_cast<float*>(smem + S::a_aug);
-        float* b_aug = reinterpret_cast<float*>(smem + S::b_aug);
-        for (int e = tid; e < kTile * 8; e += kThreads2) {
-            const int row = e >> 3, k = e & 7;
-            a_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k < 2) ? 1.f : 0.f;
-        }
-        for (int e = tid; e < N * 8; e += kThreads2) {
-            const int row = e >> 3, k = e & 7;
-            const float b = a.bias[row];
-            const float hi = tf32_hi(b);
-            b_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k == 0) ? hi : (k == 1) ? (b - hi) : 0.f;
-        }
-    }
-    if (tid == 0) {
-        for (int t = 0; t < kTiles; ++t) {
-            mbar_init(&a_ready[t], 2 * kTile);
-            mbar_init(&d_ready[t], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    bool tile_live[kTiles];
-#pragma unroll
-    for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
-
-    if (warp == kMmaWarp) {
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
-        const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-        // no-swizzle K-major descriptors: LBO = 128 B (next 4 k), SBO = 256 B (next 8 rows), version 1, layout 0
-        const uint64_t aug_fields = (8ull << 16) | (16ull << 32) | (1ull << 46);
-        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | aug_fields;
-        const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | aug_fields;
-        uint32_t phase[kTiles] = {0, 0};
-        for (int st = 0; st < total; ++st) {
-#pragma unroll
-            for (int t = 0; t < kTiles; ++t) {
-                if (!tile_live[t]) continue;
-                mbar_wait(&a_ready[t], phase[t]);
-                phase[t] ^= 1;
-                tc_fence_after();
-                if ((tid & 31) == 0) {
-                    const uint64_t dah = make_desc(smem + S::a_hi + t * kTile * 128);
-                    const uint64_t dal = make_desc(smem + S::a_lo + t * kTile * 128);
-                    const uint32_t d = tmem_base + (uint32_t)(t * N);
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
-                    if (a.split_terms == 3) {
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbl + 2 * kb, idesc, 1);
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, 1);
-                        mma_tf32(d, da_aug, db_aug, idesc, 1);            // + bias (as 1 * bias_hi + 1 * bias_lo)
-                    } else {
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, dbh + 2 * kb, idesc, kb > 0);
-                    }
-                    mma_commit(&d_ready[t]);
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        const int t = warp >> 3;                          // tile
-        const int hf = (warp >> 2) & 1;                   // which half of the hidden units
-        const int r = ((warp & 3) << 5) | (tid & 31);     // row (path) within the tile == TMEM lane
-        const int64_t path = cta_path0 + (int64_t)t * kTile + r;
-        const bool live = path < a.n_paths;
-        const int64_t lpath = live ? path : a.n_paths - 1;
-        if (tile_live[t]) {
-            float* a_hi = reinterpret_cast<float*>(smem + S::a_hi + t * kTile * 128);
-            float* a_lo = reinterpret_cast<float*>(smem + S::a_lo + t * kTile * 128);
-            // y and k1 are parked in shared memory ([h][row]: conflict-free) between stages: with 544
-            // threads the register file allows 96 registers per thread, and only the Runge-Kutta
-            // phase needs them (all loads first, then the arithmetic, then the stores)
-            float* ypark = reinterpret_cast<float*>(smem + S::park) + ((size_t)t * kH + hf * kHalf) * kTile + r;
-            float* kpark = ypark + (size_t)kTiles * kH * kTile;
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N + hf * kHalf * C);
-            const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
-            const int row_stride = cubic ? 4 * C : C;
-            const float4* crow = reinterpret_cast<const float4*>(a.control + lpath * a.n_rows * row_stride + (cubic ? C : 0));
-            const bool negate = a.sign < 0.f;
-
-            // dX/dt of interval idx at fraction frac (interpolation_cubic.py:331-336), one rounding per op
-            auto slope = [&](int idx, float frac, f2* dx2) {
-                const float4* src = crow + (size_t)idx * (row_stride / 4);
-                const float4 b0 = __ldg(src), b1 = __ldg(src + 1);
-                if (cubic) {
-                    const float4 c0 = __ldg(src + 2), c1 = __ldg(src + 3), d0 = __ldg(src + 4), d1 = __ldg(src + 5);
-                    const f2 fr = pk(frac, frac);
-                    dx2[0] = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr));
-                    dx2[1] = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr));
-                    dx2[2] = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr));
-                    dx2[3] = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr));
-                } else {
-                    dx2[0] = pk(b0.x, b0.y); dx2[1] = pk(b0.z, b0.w); dx2[2] = pk(b1.x, b1.y); dx2[3] = pk(b1.z, b1.w);
-                }
-            };
-            auto write_a = [&](const float* z) {          // this thread's 16 k-values of row r, hi / lo
-#pragma unroll
-                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
-                    float4 hi, lo;
-                    hi.x = tf32_hi(z[4 * c4 + 0]); lo.x = z[4 * c4 + 0] - hi.x;
-                    hi.y = tf32_hi(z[4 * c4 + 1]); lo.y = z[4 * c4 + 1] - hi.y;
-                    hi.z = tf32_hi(z[4 * c4 + 2]); lo.z = z[4 * c4 + 2] - hi.z;
-                    hi.w = tf32_hi(z[4 * c4 + 3]); lo.w = z[4 * c4 + 3] - hi.w;
-                    const int chunk = hf * (kHalf / 4) + c4;
-                    const uint32_t off = (uint32_t)r * 32u + (uint32_t)((chunk ^ (r & 7)) << 2);
-                    *reinterpret_cast<float4*>(a_hi + off) = hi;
-                    *reinterpret_cast<float4*>(a_lo + off) = lo;
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(&a_ready[t]);
-            };
-            auto write_out = [&](int j, const float* v) {
-                if (!live) return;
-                float4* dst = reinterpret_cast<float4*>(a.out + (path * a.n_out + j) * kH + hf * kHalf);
-#pragma unroll
-                for (int c4 = 0; c4 < kHalf / 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-            };
-
-            float s23[kHalf];
-            int jn = 0;
-            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
-            {
-                float y[kHalf];
-                const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH + hf * kHalf);
-#pragma unroll
-                for (int c4 = 0; c4 < kHalf / 4; ++c4) {
-                    const float4 v = zp[c4];
-                    y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
-                }
-#pragma unroll
-                for (int h = 0; h < kHalf; ++h) {
-                    s23[h] = 0.f;
-                    ypark[(size_t)h * kTile] = y[h];
-                    kpark[(size_t)h * kTile] = 0.f;
-                }
-                while (jn < a.n_out && next_out < 0) {
-                    write_out(jn, y);
-                    ++jn;
-                    next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
-                }
-                write_a(y);
-            }
-
-            const float third = (float)(1.0 / 3.0);
-            int step = 0, sub = 0;
-            float dt = a.step_dt[0];
-            float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
-            int idx0 = a.stage_index[0];                  // schedule entry of the current stage
-            float frac0 = a.stage_frac[0];
-            uint32_t phase = 0;
-            for (int st = 0; st < total; ++st) {
-                const bool more = st + 1 < total;
-                // ---- in the shadow of this stage's MMAs: dX/dt and the bias part of the contraction ----
-                f2 dx2[C / 2];
-                slope(idx0, frac0, dx2);
-                if (more) {                               // next stage's schedule entry: a full stage of latency hiding
-                    idx0 = a.stage_index[st + 1];
-                    frac0 = a.stage_frac[st + 1];
-                    // ... and its spline row: pull the 128-byte line towards L1/L2 now, consume it a stage later
-                    if (hf == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(crow + (size_t)idx0 * (row_stride / 4)));
-                }
-                float kv[kHalf];
-                const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && hf == 0 && r == 0 && st < 64;
-                if (tr) a.trace[st * 8 + 2] = clock64();
-                mbar_wait(&d_ready[t], phase);
-                phase ^= 1;
-                tc_fence_after();
-                if (tr) a.trace[st * 8 + 3] = clock64();
-
-                // ---- critical path: kv[h] += sum_c D[h*C + c] * dX[c] ---------------------------------
-                uint32_t va[8], vb[8];
-                tmem_ld8_issue(taddr, va);
-#pragma unroll
-                for (int h = 0; h < kHalf; ++h) {
-                    uint32_t* cur = (h & 1) ? vb : va;
-                    tmem_ld_wait(cur);
-                    if (h + 1 < kHalf) tmem_ld8_issue(taddr + (uint32_t)(C * (h + 1)), (h & 1) ? va : vb);
-                    f2 acc = mul2(pk(__uint_as_float(cur[0]), __uint_as_float(cur[1])), dx2[0]);
-                    acc = fma2(pk(__uint_as_float(cur[2]), __uint_as_float(cur[3])), dx2[1], acc);
-                    acc = fma2(pk(__uint_as_float(cur[4]), __uint_as_float(cur[5])), dx2[2], acc);
-                    acc = fma2(pk(__uint_as_float(cur[6]), __uint_as_float(cur[7])), dx2[3], acc);
-                    float lo, hi;
-                    upk(acc, lo, hi);
-                    const float sum = lo + hi;
-                    kv[h] = negate ? -sum : sum;
-                }
-
-                if (tr) a.trace[st * 8 + 4] = clock64();
-                // ---- Runge-Kutta combination, one rounding per operation, two hidden units per instruction
-                bool step_done = false;
-                float zn[kHalf], y[kHalf], k1[kHalf];
-#pragma unroll
-                for (int h = 0; h < kHalf; ++h) y[h] = ypark[(size_t)h * kTile];
-                const f2 dt2 = pk(dt, dt);
-                if (a.method == TCDE_RK4_38) {
-                    const f2 th2 = pk(third, third);
-                    if (sub != 0) {
-#pragma unroll
-                        for (int h = 0; h < kHalf; ++h) k1[h] = kpark[(size_t)h * kTile];
-                    }
-                    if (sub == 0) {
-#pragma unroll
-                        for (int h = 0; h < kHalf; h += 2)
-                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, pk(kv[h], kv[h + 1])), th2)), zn[h], zn[h + 1]);
-#pragma unroll
-                        for (int h = 0; h < kHalf; ++h) kpark[(size_t)h * kTile] = kv[h];
-                    } else if (sub == 1) {
-#pragma unroll
-                        for (int h = 0; h < kHalf; h += 2) {
-                            const f2 k2 = pk(kv[h], kv[h + 1]);
-                            s23[h] = kv[h];
-                            s23[h + 1] = kv[h + 1];
-                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(k2, mul2(pk(k1[h], k1[h + 1]), th2)))), zn[h], zn[h + 1]);
-                        }
-                    } else if (sub == 2) {
-#pragma unroll
-                        for (int h = 0; h < kHalf; h += 2) {
-                            const f2 k2 = pk(s23[h], s23[h + 1]);
-                            const f2 k3 = pk(kv[h], kv[h + 1]);
-                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(pk(k1[h], k1[h + 1]), k2), k3))), zn[h], zn[h + 1]);
-                            upk(add2(k2, k3), s23[h], s23[h + 1]);
-                        }
-                    } else {
-                        const f2 three = pk(3.f, 3.f), eighth = pk(0.125f, 0.125f);
-#pragma unroll
-                        for (int h = 0; h < kHalf; h += 2) {
-                            const f2 sum = add2(add2(pk(k1[h], k1[h + 1]), mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
-                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(sum, dt2), eighth)), zn[h], zn[h + 1]);
-                        }
-                        step_done = true;
-                    }
-                } else if (a.method == TCDE_MIDPOINT) {
-                    if (sub == 0) {
-                        const float half = E::mul(0.5f, dt);
-#pragma unroll
-                        for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(kv[h], half));
-                    } else {
-#pragma unroll
-                        for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
-                        step_done = true;
-                    }
-                } else {
-#pragma unroll
-                    for (int h = 0; h < kHalf; ++h) zn[h] = E::add(y[h], E::mul(dt, kv[h]));
-                    step_done = true;
-                }
-                if (tr) a.trace[st * 8 + 5] = clock64();
-                if (more) write_a(zn);                    // hand the next stage to the tensor core first ...
-                if (tr) a.trace[st * 8 + 6] = clock64();
-                if (step_done) {                          // ... then the bookkeeping that nobody waits for
-                    while (next_out == step) {
-                        const int mode = a.out_mode[jn];
-                        if (mode == 0) write_out(jn, y);
-                        else if (mode == 1) write_out(jn, zn);
-                        else {
-                            const float slope_w = a.out_slope[jn];
-                            float v[kHalf];
-#pragma unroll
-                            for (int h = 0; h < kHalf; ++h) v[h] = E::add(y[h], E::mul(slope_w, E::sub(zn[h], y[h])));
-                            write_out(jn, v);
-                        }
-                        ++jn;
-                        next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
-                    }
-#pragma unroll
-                    for (int h = 0; h < kHalf; ++h) ypark[(size_t)h * kTile] = zn[h];
-                    ++step;
-                    sub = 0;
-                    dt = dt_next;
-                    if (step + 1 < a.n_steps) dt_next = a.step_dt[step + 1];
-                } else {
-                    ++sub;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
-}
-
-}  // namespace v2
 
 }  // namespace umma
 
 bool solve_umma_supported(int H, int C) { return H == umma::kH && C == 8; }
 
-int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t stream) {
+int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream) {
     TCDE_CHECK_SUPPORTED(solve_umma_supported(H, C), "tensor-core solve: built for hidden=32, channels=8 (got %d, %d)", H, C);
     TCDE_CHECK_SUPPORTED((reinterpret_cast<uintptr_t>(a.control) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.z0) & 15) == 0 &&
                              (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
@@ -926,17 +509,10 @@ int solve_umma_f32(const UmmaArgs& a, int H, int C, int version, cudaStream_t st
     const int64_t per_cta = umma::kTile * umma::kTiles;
     const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
     TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
-    if (version == 1) {
-        auto kern = a.trace ? umma::cdeint_umma_kernel<8, true> : umma::cdeint_umma_kernel<8, false>;
-        constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
-        TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
-    } else {
-        auto kern = a.trace ? umma::v2::cdeint_umma2_kernel<8, true> : umma::v2::cdeint_umma2_kernel<8, false>;
-        constexpr int smem = umma::v2::Smem2<256>::total + 1024;
-        TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(unsigned)ctas, umma::v2::kThreads2, smem, stream>>>(a);
-    }
+    auto kern = a.trace ? umma::cdeint_umma_kernel<8, true> : umma::cdeint_umma_kernel<8, false>;
+    constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }
