@@ -726,49 +726,8 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
             if (use_bulk && tid == 0) bulk_wait_read<1>();
             __syncthreads();
             T* ot = buf ? ot1 : ot0;
-            if (vec4) {                  // (interval, 4 channels) per thread, 128-bit staged stores
-                const int Q = C >> 2;
-                float4* ot4 = reinterpret_cast<float4*>(ot);
-                int i = tid / Q, q = tid - (tid / Q) * Q;
-                const int dq_i = kThreads / Q, dq_q = kThreads - dq_i * Q;
-                for (int e = tid; e < nr * Q; e += kThreads) {
-                    const int r = r0 + i;
-                    const T rd = rdt[r], rd2 = rdt2[r];
-                    float av[4], bv[4], cv[4], dv[4];
-                    const f2 rdp = pk2((float)rd, (float)rd), rd2p = pk2((float)rd2, (float)rd2);
-#pragma unroll
-                    for (int j = 0; j < 4; j += 2) {              // two channels per packed instruction
-                        const float* xr0 = reinterpret_cast<const float*>(xs) + (4 * q + j) * Lp + r;
-                        const float* kr0 = reinterpret_cast<const float*>(ks) + (4 * q + j) * Lp + r;
-                        const f2 xl = pk2(xr0[0], xr0[Lp]), xh = pk2(xr0[1], xr0[Lp + 1]);
-                        const f2 kl = pk2(kr0[0], kr0[Lp]), kh = pk2(kr0[1], kr0[Lp + 1]);
-                        const f2 six = mul2(pk2(2.f, 2.f), mul2(pk2(3.f, 3.f), sub2(xh, xl)));
-                        const f2 sr = mul2(six, rdp);
-                        const f2 c2 = mul2(sub2(sub2(sr, mul2(pk2(4.f, 4.f), kl)), mul2(pk2(2.f, 2.f), kh)), rdp);   // :45-47
-                        const f2 d3 = mul2(sub2(mul2(pk2(3.f, 3.f), add2(kl, kh)), sr), rd2p);                          // :48-50
-                        upk2(xl, av[j], av[j + 1]);
-                        upk2(kl, bv[j], bv[j + 1]);
-                        upk2(c2, cv[j], cv[j + 1]);
-                        upk2(d3, dv[j], dv[j + 1]);
-                    }
-                    float4* row = ot4 + (size_t)i * (4 * Q) + q;
-#pragma unroll
-                    for (int kq = 0; kq < 4; ++kq) {
-                        const int w = (kq + i) & 3;
-                        float4 v;
-                        if (w == 0) v = make_float4(av[0], av[1], av[2], av[3]);
-                        else if (w == 1) v = make_float4(bv[0], bv[1], bv[2], bv[3]);
-                        else if (w == 2) v = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                        else v = make_float4(dv[0], dv[1], dv[2], dv[3]);
-                        row[w * Q] = v;
-                    }
-                    i += dq_i;
-                    q += dq_q;
-                    if (q >= Q) { q -= Q; ++i; }
-                }
-            }
             int i = tid / C, c = tid - (tid / C) * C;
-            for (int e = vec4 ? nr * C : tid; e < nr * C; e += kThreads) {
+            for (int e = tid; e < nr * C; e += kThreads) {
                 const int r = r0 + i;
                 const T* xr = xs + c * Lp + r;
                 const T* kr = ks + c * Lp + r;
