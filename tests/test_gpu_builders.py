@@ -116,6 +116,33 @@ def test_edge_cases():
                 O.hermite_backward_difference_coeffs(xt.cpu().contiguous()))
 
 
+@pytest.mark.parametrize("shape", [(70, 256, 8), (9, 100, 4), (5, 33, 12), (3, 20, 64), (4, 3, 8), (2, 5, 128),
+                                   (131, 17, 72), (40, 1000, 4), (1, 64, 8)])
+@pytest.mark.parametrize("knots", ["unit", "uneven", "stiff"])
+def test_natural_cubic_kernel_variants(shape, knots):
+    """fp32 with channels % 4 == 0 takes the warp-per-path kernel (variant 0); it must agree with the CTA-per-path
+    kernel (variant 2), the sequential one-thread-per-series kernel (variant 1) and the oracle.  'stiff' knots
+    (spacings over three decades) make the warm-up windows long and uneven."""
+    from torchcde_b200 import _lib
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=gen, dtype=torch.float64).to(torch.float32)
+    if knots == "unit":
+        t = None
+    elif knots == "uneven":
+        t = (torch.rand(shape[-2], generator=gen, dtype=torch.float64) + 0.1).cumsum(0).to(torch.float32)
+    else:
+        t = (10.0 ** (3 * torch.rand(shape[-2], generator=gen, dtype=torch.float64) - 2)).cumsum(0).to(torch.float32)
+    want = O.natural_cubic_coeffs(x, t, 1)
+    td = None if t is None else t.to(DEV)
+    try:
+        for variant in (0, 2, 1):
+            _lib.call("tcde_set_natural_variant", variant)
+            got = cde.natural_cubic_coeffs(x.to(DEV), td).cpu()
+            assert _close_ulps(got, want, ulps=256 if knots == "stiff" else 64), (variant, shape, knots)
+    finally:
+        _lib.call("tcde_set_natural_variant", 0)
+
+
 def test_hermite_unit_time_closed_form():
     """The reference's independent restatement for unit knots (test_hermite_cubic.py:5-22):
     2c = 4 (d_next - d_prev), 3d = -3 (d_next - d_prev)."""

@@ -774,6 +774,286 @@ natural_win_kernel(const T* __restrict__ x, const T* __restrict__ ws, T* __restr
     if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
 }
 
+// Natural cubic spline, one WARP per path (fp32, channels % 4 == 0).  No CTA barrier after the
+// prologue: a warp loads its path with 128-bit loads into its own shared-memory tile kept in
+// the global [knot][channel] order, sweeps it with lane = (channel pair, chunk of G knots) --
+// 64-bit shared loads feed the packed fp32x2 pipe directly -- and writes the coefficient rows
+// with four 128-bit stores per (interval, 4 channels).  The back substitution overwrites the
+// forward-sweep values in place (warm-up reads of the neighbouring chunk happen before a
+// __syncwarp, the chunk's own stores after it), so a path needs two tiles, not three.
+// Chunk c of a tile starts at word c * (G * C + padw) with padw chosen so that consecutive
+// chunks start C banks apart: the sweeps' strided accesses are conflict free.  The per-knot
+// constants are stored already duplicated for the packed pipe, at index i + i / G (one slot of
+// padding per chunk, same reason).  ~2.2 K warp-instructions per path against ~10 K for the
+// CTA-per-path kernel (whose chunks of 4 knots re-ran a 16-knot warm-up each).
+static constexpr int kNatPrefetch = 16;     // 128-bit loads per lane kept in flight for the next path
+static constexpr int kNatMaxWarps = 12;
+
+__global__ void __launch_bounds__(32 * kNatMaxWarps)
+natural_warp_kernel(const float* __restrict__ x, const float* __restrict__ ws, float* __restrict__ out,
+                    int64_t n_paths, int L, int C, int lgG, int padw, int tile_words, int stage_words,
+                    int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int G = 1 << lgG;
+    const int nct = (L + G - 1) >> lgG;
+    const int Lc = L + nct + 1;
+    const int Lc2 = (Lc + 1) & ~1;
+    float2* cA = reinterpret_cast<float2*>(smem_raw);          // [i + i/G] = (rdt2, mult)
+    float2* cB = cA + Lc2;                                      // [i + i/G] = (rdt, rnd)
+    float2* cC = cB + Lc2;                                      // [i] = (rdt, rdt2)
+    float* tiles = reinterpret_cast<float*>(cC + ((L + 1) & ~1));
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float rd = ws[i], rd2 = ws[L + i], m = ws[2 * L + i], rn = ws[3 * L + i];
+        const int pi = i + (i >> lgG);
+        cA[pi] = make_float2(rd2, m);
+        cB[pi] = make_float2(rd, rn);
+        cC[i] = make_float2(rd, rd2);
+    }
+    __syncthreads();
+    const int wf = (int)ws[4 * L], wb = (int)ws[4 * L + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    float* xs = tiles + (size_t)warp * (2 * tile_words + stage_words);
+    float* fk = xs + tile_words;
+    float* stage = fk + tile_words;                     // stage_words: coefficient rows staged for a bulk store
+    const int C2 = C >> 1, Q = C >> 2;
+    const int n_items = C2 * nct;
+    const int n_vec = L * Q;
+    const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
+    const int row_step = C + padw;                     // from the last knot of a chunk to the first of the next
+    const f2 three = pk2(3.f, 3.f), two = pk2(2.f, 2.f), four = pk2(4.f, 4.f);
+    bool saw_nan = false;
+    const int RR = stage_words / (4 * C);              // rows per bulk store
+    int rl_pre[2], q_pre[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        rl_pre[u] = (lane + 32 * u) / Q;
+        q_pre[u] = lane + 32 * u - rl_pre[u] * Q;
+    }
+    auto word = [&](int i) { return i * C + (i >> lgG) * padw; };
+
+    // The next path's knots are requested before the current path is swept: the DRAM latency of a
+    // warp's only global loads is covered by its own arithmetic, not by other warps.
+    float4 pre[kNatPrefetch];
+    auto request = [&](int64_t path) {
+        const float4* xg4 = reinterpret_cast<const float4*>(x + path * (int64_t)L * C);
+#pragma unroll
+        for (int k = 0; k < kNatPrefetch; ++k)
+            if (lane + 32 * k < n_vec) pre[k] = __ldg(xg4 + lane + 32 * k);
+    };
+    const int64_t stride = (int64_t)gridDim.x * n_warps;
+    int64_t p = (int64_t)blockIdx.x * n_warps + warp;
+    if (p < n_paths) request(p);
+
+    for (; p < n_paths; p += stride) {
+        __syncwarp();                                   // the previous path's coefficient phase has read xs / fk
+        {
+            int i = lane / Q, q = lane - (lane / Q) * Q;
+#pragma unroll
+            for (int k = 0; k < kNatPrefetch; ++k) {
+                if (lane + 32 * k < n_vec) {
+                    const float4 v = pre[k];
+                    saw_nan |= is_nan(v.x) | is_nan(v.y) | is_nan(v.z) | is_nan(v.w);
+                    *reinterpret_cast<float4*>(xs + word(i) + 4 * q) = v;
+                }
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+            const float4* xg4 = reinterpret_cast<const float4*>(x + p * (int64_t)L * C);
+#pragma unroll 4
+            for (int e = lane + 32 * kNatPrefetch; e < n_vec; e += 32) {       // longer paths: the rest, directly
+                const float4 v = __ldg(xg4 + e);
+                saw_nan |= is_nan(v.x) | is_nan(v.y) | is_nan(v.z) | is_nan(v.w);
+                *reinterpret_cast<float4*>(xs + word(i) + 4 * q) = v;
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+        }
+        if (p + stride < n_paths) request(p + stride);
+        __syncwarp();
+        for (int base = 0; base < n_items; base += 32) {             // forward sweep (misc.py:58-61)
+            const int it = base + lane;
+            if (it >= n_items) continue;
+            const int pr = it % C2, j = it / C2;
+            const int g0 = j << lgG, g1 = min(g0 + G, L);
+            int i = max(g0 - wf, 0);
+            const float* px = xs + 2 * pr + word(i);               // x[i]; the forward value of knot i goes to
+            const float2* pa = cA + i + (i >> lgG);                // px + tile_words
+            f2 f = pk2(0.f, 0.f), sc_prev = pk2(0.f, 0.f);
+            f2 x_lo = *reinterpret_cast<const f2*>(px);
+            if (i > 0) {
+                const float2 a = cA[i - 1 + ((i - 1) >> lgG)];
+                const f2 x_before = *reinterpret_cast<const f2*>(xs + 2 * pr + word(i - 1));
+                sc_prev = mul2(mul2(three, sub2(x_lo, x_before)), pk2(a.x, a.x));
+            }
+            // scaled difference 3 (x[i+1] - x[i]) / dt_i^2; rdt2[L-1] = 0 closes the system (cubic.py:36-39)
+            auto knot = [&](const f2 x_hi, const float2 a, float* dst, bool keep) {
+                const f2 sc = mul2(mul2(three, sub2(x_hi, x_lo)), pk2(a.x, a.x));
+                x_lo = x_hi;
+                f = sub2(add2(sc, sc_prev), mul2(pk2(a.y, a.y), f));
+                sc_prev = sc;
+                if (keep) *reinterpret_cast<f2*>(dst) = f;
+            };
+            while (i < g1) {                                         // chunk by chunk: warm-up chunks, then its own
+                const int seg_end = min((i | (G - 1)) + 1, g1);
+                const bool keep = i >= g0;
+                int r = seg_end - 1 - i;
+                for (; r >= 4; r -= 4) {                             // loads of four knots ahead of their stores
+                    f2 xh[4];
+                    float2 aa[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        xh[u] = *reinterpret_cast<const f2*>(px + (u + 1) * C);
+                        aa[u] = pa[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) knot(xh[u], aa[u], const_cast<float*>(px) + u * C + tile_words, keep);
+                    px += 4 * C;
+                    pa += 4;
+                }
+                for (; r > 0; --r) {
+                    knot(*reinterpret_cast<const f2*>(px + C), *pa, const_cast<float*>(px) + tile_words, keep);
+                    px += C;
+                    ++pa;
+                }
+                const int step = (seg_end == L) ? 0 : row_step;      // the right neighbour of the last knot is itself
+                knot(*reinterpret_cast<const f2*>(px + step), *pa, const_cast<float*>(px) + tile_words, keep);
+                px += step;
+                pa += 2;
+                i = seg_end;
+            }
+        }
+        __syncwarp();
+        for (int base = 0; base < n_items; base += 32) {             // back substitution (misc.py:63-65), in place
+            const int it = base + lane;
+            const bool active = it < n_items;
+            const int pr = active ? it % C2 : 0, j = active ? it / C2 : 0;
+            const int g0 = j << lgG, g1 = min(g0 + G, L);
+            int i = min(g1 - 1 + wb, L - 1);
+            float* pf = fk + 2 * pr + word(i);
+            const float2* pb = cB + i + (i >> lgG);
+            f2 k = pk2(0.f, 0.f);
+            if (active) {
+                while (i >= g1) {                                    // warm-up in the chunks to the right: reads only
+                    const int seg_lo = max(i & ~(G - 1), g1);        // g1 is a chunk boundary whenever this loop runs
+                    for (; i > seg_lo; --i) {
+                        const float2 b = *pb;
+                        k = mul2(sub2(*reinterpret_cast<const f2*>(pf), mul2(pk2(b.x, b.x), k)), pk2(b.y, b.y));
+                        pf -= C;
+                        --pb;
+                    }
+                    const float2 b = *pb;
+                    k = mul2(sub2(*reinterpret_cast<const f2*>(pf), mul2(pk2(b.x, b.x), k)), pk2(b.y, b.y));
+                    pf -= row_step;
+                    pb -= 2;
+                    i = seg_lo - 1;
+                }
+            }
+            __syncwarp();
+            if (active) {
+                for (; i >= g0 + 3; i -= 4) {                       // loads of four knots ahead of their stores
+                    f2 fv[4];
+                    float2 bb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        fv[u] = *reinterpret_cast<const f2*>(pf - u * C);
+                        bb[u] = *(pb - u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        k = mul2(sub2(fv[u], mul2(pk2(bb[u].x, bb[u].x), k)), pk2(bb[u].y, bb[u].y));
+                        *reinterpret_cast<f2*>(pf - u * C) = k;
+                    }
+                    pf -= 4 * C;
+                    pb -= 4;
+                }
+                for (; i >= g0; --i) {
+                    const float2 b = *pb;
+                    k = mul2(sub2(*reinterpret_cast<const f2*>(pf), mul2(pk2(b.x, b.x), k)), pk2(b.y, b.y));
+                    *reinterpret_cast<f2*>(pf) = k;
+                    pf -= C;
+                    --pb;
+                }
+            }
+        }
+        __syncwarp();
+        {
+            // coefficient rows: RR whole rows per round (two items per lane, loads of both ahead of the math), staged
+            // in shared memory exactly as they lie in global memory and written by one bulk (TMA) store of the warp's
+            // elected lane.  Lane = (row, 4 channels); its four 16-byte blocks go to the staging row in an order
+            // rotated by the row number, which spreads the lanes of one store instruction over the banks (rows are
+            // 16 C bytes apart).  The staging buffer is reused once the previous bulk store has read it.
+            float* og = out + p * (int64_t)(L - 1) * 4 * C;
+            for (int r0 = 0; r0 < L - 1; r0 += RR) {
+                const int n_it = min(RR, L - 1 - r0) * Q;
+                for (int base = 0; base < n_it; base += 64) {
+                    int rl[2], qq[2];
+                    bool valid[2];
+                    float4 xl[2], xh[2], kl[2], kh[2];
+                    float2 rr[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int it = base + lane + 32 * u;
+                        rl[u] = base == 0 ? rl_pre[u] : it / Q;
+                        qq[u] = base == 0 ? q_pre[u] : it - (it / Q) * Q;
+                        valid[u] = it < n_it;
+                        if (valid[u]) {
+                            const int i = r0 + rl[u];
+                            const int w0 = word(i) + 4 * qq[u], w1 = word(i + 1) + 4 * qq[u];
+                            xl[u] = *reinterpret_cast<const float4*>(xs + w0);
+                            xh[u] = *reinterpret_cast<const float4*>(xs + w1);
+                            kl[u] = *reinterpret_cast<const float4*>(fk + w0);
+                            kh[u] = *reinterpret_cast<const float4*>(fk + w1);
+                            rr[u] = cC[i];
+                        }
+                    }
+                    if (base == 0) {
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (!valid[u]) continue;
+                        const f2 rdp = pk2(rr[u].x, rr[u].x), rd2p = pk2(rr[u].y, rr[u].y);
+                        float4 cv, dv;
+                        {
+                            const f2 l = pk2(kl[u].x, kl[u].y), h = pk2(kh[u].x, kh[u].y);
+                            const f2 sr = mul2(mul2(two, mul2(three, sub2(pk2(xh[u].x, xh[u].y), pk2(xl[u].x, xl[u].y)))), rdp);
+                            upk2(mul2(sub2(sub2(sr, mul2(four, l)), mul2(two, h)), rdp), cv.x, cv.y);   // cubic.py:45-47
+                            upk2(mul2(sub2(mul2(three, add2(l, h)), sr), rd2p), dv.x, dv.y);             // cubic.py:48-50
+                        }
+                        {
+                            const f2 l = pk2(kl[u].z, kl[u].w), h = pk2(kh[u].z, kh[u].w);
+                            const f2 sr = mul2(mul2(two, mul2(three, sub2(pk2(xh[u].z, xh[u].w), pk2(xl[u].z, xl[u].w)))), rdp);
+                            upk2(mul2(sub2(sub2(sr, mul2(four, l)), mul2(two, h)), rdp), cv.z, cv.w);
+                            upk2(mul2(sub2(mul2(three, add2(l, h)), sr), rd2p), dv.z, dv.w);
+                        }
+                        // rotate (a, b, 2c, 3d) left by rl & 3: two conditional stages of register selects
+                        const bool r1 = rl[u] & 1, r2 = rl[u] & 2;
+                        const float4 v0 = r1 ? kl[u] : xl[u], v1 = r1 ? cv : kl[u], v2 = r1 ? dv : cv, v3 = r1 ? xl[u] : dv;
+                        const float4 u0 = r2 ? v2 : v0, u1 = r2 ? v3 : v1, u2 = r2 ? v0 : v2, u3 = r2 ? v1 : v3;
+                        float4* row = reinterpret_cast<float4*>(stage) + (size_t)rl[u] * (4 * Q) + qq[u];
+                        const int b0 = rl[u] & 3;
+                        row[b0 * Q] = u0;
+                        row[((b0 + 1) & 3) * Q] = u1;
+                        row[((b0 + 2) & 3) * Q] = u2;
+                        row[((b0 + 3) & 3) * Q] = u3;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(og + (size_t)r0 * 4 * C, stage, (uint32_t)(n_it * 64));     // an item is 4 x 16 bytes
+                    bulk_commit();
+                }
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
+}
+
 // One CTA per group of S paths.  Phase 1: coalesced load, transposed into shared memory as
 // [series][knot] so that the thread that owns a series walks contiguous words.  Phase 2: one
 // thread per series runs the forward sweep and the back substitution in shared memory.
@@ -1057,7 +1337,8 @@ nan_flag_kernel(const T* __restrict__ x, int64_t n, int32_t* __restrict__ flags)
 // launchers
 // =========================================================================================
 static int g_fill_variant = 0;        // 0 = warp-per-path gap fill when it fits, 1 = one thread per series
-static int g_natural_variant = 0;     // 0 = windowed parallel sweeps when they fit, 1 = one thread per series
+static int g_natural_variant = 0;     // 0 = warp per path / windowed CTA sweeps when they fit, 1 = one thread per
+                                      // series, 2 = never the warp-per-path kernel
 
 static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t n_items) {
     int per_sm = 1;
@@ -1118,6 +1399,36 @@ static int launch_natural(const T* x, const T* t, T* out, T* ws, int64_t n_paths
     int TR = (int)(8192 / row_bytes);
     if (TR < 1) TR = 1;
     if (TR > L - 1) TR = L - 1;
+    if constexpr (sizeof(T) == 4) {
+        // warp per path: fp32, 128-bit rows, two tiles per warp in shared memory
+        if ((C & 3) == 0 && L > 2 && aligned16(out) && aligned16(x) && g_natural_variant == 0) {
+            const int C2 = C / 2;
+            const int n_chunks = C2 >= 32 ? 1 : 32 / C2;
+            int lgG = 0;
+            while ((1 << lgG) * n_chunks < L) ++lgG;
+            const int G = 1 << lgG;
+            const int nct = (L + G - 1) / G;
+            const int padw = (int)((((int64_t)C - (int64_t)G * C) % 32 + 32) % 32);
+            const int tile_words = L * C + nct * padw;
+            const int rows_per_round = C / 4 >= 32 ? 2 : 64 / (C / 4);       // two (row, 4 channels) items per lane
+            const int stage_words = rows_per_round * 4 * C;
+            const size_t fixed = (size_t)2 * ((L + nct + 2) & ~1) * 8 + (size_t)((L + 1) & ~1) * 8;
+            const size_t per_warp = (size_t)(2 * tile_words + stage_words) * 4;
+            int wpc = fixed < 220 * 1024 ? (int)((220 * 1024 - fixed) / per_warp) : 0;
+            if (wpc > kNatMaxWarps) wpc = kNatMaxWarps;
+            if (wpc >= 2) {
+                const size_t smem_k = fixed + wpc * per_warp;
+                auto kw = natural_warp_kernel;
+                TCDE_CHECK_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+                int64_t grid = (n_paths + wpc - 1) / wpc;
+                if (grid > sm_count()) grid = sm_count();
+                kw<<<(int)grid, 32 * wpc, smem_k, stream>>>((const float*)x, (const float*)ws, (float*)out, n_paths, L, C,
+                                                           lgG, padw, tile_words, stage_words, flags);
+                TCDE_CHECK_CUDA(cudaGetLastError());
+                return TCDE_OK;
+            }
+        }
+    }
     {
         // parallel windowed sweeps: one path per CTA iteration, thread = (series, chunk of G knots)
         const int Lpw = ((L + 31) / 32) * 32 + 1;
@@ -1315,7 +1626,8 @@ extern "C" int tcde_nan_flag(const void* x, int64_t n, int dtype, int32_t* flags
 }
 
 extern "C" int tcde_set_natural_variant(int variant) {
-    TCDE_CHECK_ARG(variant == 0 || variant == 1, "variant=%d (0 parallel kernels, 1 one thread per series)", variant);
+    TCDE_CHECK_ARG(variant >= 0 && variant <= 2,
+                   "variant=%d (0 parallel kernels, 1 one thread per series, 2 CTA-per-path natural kernel)", variant);
     g_natural_variant = variant;
     g_fill_variant = variant;
     return TCDE_OK;
