@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCDE_ABI_VERSION 1
+#define TCDE_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TCDE_API __attribute__((visibility("default")))
@@ -72,9 +72,11 @@ TCDE_API int tcde_hermite_bdiff_coeffs(const void* x, const void* t, void* coeff
 
 /* linear_interpolation_coeffs with missing values, per series
  * (interpolation_linear.py:13-84): all-NaN -> zeros; missing ends take the first / last
- * observation; interior gaps are interpolated in time.  x -> out, same shape.  Bit-identical. */
+ * observation; interior gaps are interpolated in time.  x -> out, same shape.  Bit-identical.
+ * flags (optional): TCDE_FLAG_NAN_SEEN is set when x held a NaN -- without it out is a copy of x and the
+ * caller returns x itself like the reference (interpolation_linear.py:169-171), with no separate isnan pass. */
 TCDE_API int tcde_linear_fill(const void* x, const void* t, void* out, int64_t n_paths, int64_t length,
-                     int64_t channels, int dtype, void* stream);
+                     int64_t channels, int dtype, int32_t* flags, void* stream);
 
 /* torch.isnan(x).any() (the branch selector at interpolation_linear.py:169 and
  * interpolation_cubic.py:176) over n elements: sets TCDE_FLAG_NAN_SEEN in *flags. */

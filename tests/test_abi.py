@@ -23,7 +23,7 @@ def test_library_exports_every_symbol():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.tcde_abi_version() == 1
+    assert lib.tcde_abi_version() == 2
 
 
 def test_argument_errors_do_not_need_a_gpu():
@@ -32,7 +32,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.tcde_hermite_bdiff_coeffs(None, None, None, 1, 4, 2, 0, None, None) == -1
     assert b"null" in lib.tcde_last_error()
     with pytest.raises(ValueError):
-        _lib.call("tcde_linear_fill", None, None, None, 1, 4, 2, 0, None)
+        _lib.call("tcde_linear_fill", None, None, None, 1, 4, 2, 0, None, None)
 
 
 def test_product_path_never_imports_the_oracle():

@@ -143,6 +143,37 @@ def test_natural_cubic_kernel_variants(shape, knots):
         _lib.call("tcde_set_natural_variant", 0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(70, 256, 8), (9, 100, 4), (5, 33, 12), (3, 20, 32), (4, 3, 8), (6, 2, 1),
+                                   (131, 17, 7), (40, 1000, 4), (3, 64, 1), (2, 2000, 16)])
+@pytest.mark.parametrize("rate", [0.3, 0.9])
+def test_linear_fill_kernel_variants(dtype, shape, rate):
+    """Channels <= 32 take the scan kernel (variant 0); it must give the bits of the ballot kernel (variant 2), of
+    the one-thread-per-series kernel (variant 1) and of the oracle -- including all-NaN series, leading / trailing
+    gaps, gaps longer than a chunk and -0.0 observations next to an imputed end point."""
+    from torchcde_b200 import _lib
+    gen = torch.Generator().manual_seed(sum(shape) + int(rate * 10))
+    x = torch.randn(shape, generator=gen, dtype=torch.float64).to(dtype)
+    x[torch.rand(shape, generator=gen) < 0.05] = -0.0
+    x[torch.rand(shape, generator=gen) < rate] = float("nan")
+    x[0, :, 0] = float("nan")                              # one series with nothing observed
+    if shape[1] > 2:
+        x[-1, 0, :] = float("nan")                         # leading / trailing gaps on a whole path
+        x[-1, -1, :] = float("nan")
+    for t in (None, (torch.rand(shape[-2], generator=gen, dtype=torch.float64) + 0.1).cumsum(0).to(dtype)):
+        want = O.linear_knots(x, t)
+        td = None if t is None else t.to(DEV)
+        try:
+            for variant in (0, 2, 1):
+                _lib.call("tcde_set_natural_variant", variant)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    got = cde.linear_interpolation_coeffs(x.to(DEV), td).cpu()
+                assert same(got, want), (variant, shape, rate, t is None)
+        finally:
+            _lib.call("tcde_set_natural_variant", 0)
+
+
 def test_hermite_unit_time_closed_form():
     """The reference's independent restatement for unit knots (test_hermite_cubic.py:5-22):
     2c = 4 (d_next - d_prev), 3d = -3 (d_next - d_prev)."""

@@ -81,11 +81,11 @@ def _has_nan(flat):
     return bool(flags.item() & _lib.FLAG_NAN_SEEN)
 
 
-def _fill(flat, knots):
+def _fill(flat, knots, flags=None):
     out = torch.empty_like(flat)
     p, length, channels = flat.shape
     _lib.call("tcde_linear_fill", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length, channels,
-              _lib.dtype_code(flat.dtype), _lib.stream_of(flat))
+              _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
     return out
 
 
@@ -155,10 +155,17 @@ def linear_interpolation_coeffs(x, t=None, rectilinear=None):
             t_full = validate_input_path(x, t)
             has_nan = starts_with_nan
         else:
+            # one pass: the fill kernel also reports whether there was anything to fill (linear.py:169-171)
             t_full = validate_input_path(x, t)
-            _lib.dtype_code(x.dtype)
             flat, batch = _paths(x)
-            has_nan = _has_nan(flat)
+            if flat.numel() == 0:
+                return x
+            knots = None if t is None else _knots_arg(t_full, x)
+            flags = _flags(flat)
+            out = _fill(flat, knots, flags)
+            if not flags.item() & _lib.FLAG_NAN_SEEN:
+                return x
+            return out.view(*batch, x.size(-2), x.size(-1))
         if not has_nan:
             return x
         flat, batch = _paths(x)

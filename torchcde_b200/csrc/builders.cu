@@ -420,6 +420,181 @@ linear_fill_warp_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
     }
 }
 
+// Scan variant of the gap fill: lane = (channel, chunk of G consecutive positions) of one path, for
+// channels <= 32.  ncu on the ballot kernel above: 115 warp-instructions per 32 elements, issue
+// bound at 19% of HBM peak.  Here the warp's tile stays in the global [position][channel] order
+// (128-bit loads and stores on both sides, chunks padded so that the 32 lanes hit 32 banks) and
+// every lane walks its chunk backward once: each hole is overwritten with a NaN whose payload holds
+// the distances to the next observation and to the next hole of the chunk, which threads the holes
+// into a list.  A few shuffles hand every chunk the nearest observation of the chunks before and
+// after it.  Then the lane hops along its list of holes only (30% of the positions in the
+// benchmark) and replaces each by the reference's interpolation formula; the end points of a gap
+// are fetched once per gap.
+template <typename T> struct nan_code;
+template <> struct nan_code<float> {
+    static constexpr uint32_t quiet = 0x7FC00000u;
+    __device__ static int get(float v) { return (int)(__float_as_uint(v) & 0x3FFFFFu); }
+    __device__ static float make(int i) { return __uint_as_float(quiet | (uint32_t)i); }
+};
+template <> struct nan_code<double> {
+    static constexpr unsigned long long quiet = 0x7FF8000000000000ull;
+    __device__ static int get(double v) { return (int)((unsigned long long)__double_as_longlong(v) & 0x3FFFFFull); }
+    __device__ static double make(int i) { return __longlong_as_double((long long)(quiet | (unsigned long long)i)); }
+};
+constexpr int kFillNone = 0x3FFFFF;          // no observation
+constexpr int kFillDist = 11;                // payload = distance to next observation | distance to next hole << 11
+
+template <typename T, bool UNIT>
+__global__ void __launch_bounds__(kThreads)
+linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_paths, int L,
+                        int C, int lgG, int padw, int tile_words, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using E = exact<T>;
+    T* ts = reinterpret_cast<T*>(smem_raw);                 // knot times (absent for unit knots)
+    T* tiles = ts + (UNIT ? 0 : ((L + 3) & ~3));
+    if (!UNIT) {
+        for (int i = threadIdx.x; i < L; i += blockDim.x) ts[i] = t[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* tile = tiles + (size_t)warp * tile_words;
+    const int G = 1 << lgG;
+    const int nch = (L + G - 1) >> lgG;                     // chunks in use (<= 32 / C)
+    const int c = lane % C, j = lane / C;
+    const bool active = j < nch;
+    const int g0 = j << lgG, g1 = min(g0 + G, L);
+    const unsigned full = 0xffffffffu;
+    auto word = [&](int i) { return i * C + (i >> lgG) * padw; };
+    auto time_of = [&](int i) -> T { return UNIT ? T(i) : ts[i]; };
+    const bool vec4 = (sizeof(T) == 4) && ((C & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int Q = C >> 2;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / 32);
+    bool saw_nan = false;
+
+    for (int64_t p = (int64_t)blockIdx.x * (kThreads / 32) + warp; p < n_paths; p += warps_total) {
+        const T* xg = x + p * (int64_t)L * C;
+        T* og = out + p * (int64_t)L * C;
+        __syncwarp();                                       // the previous path has been copied out
+        if (vec4) {
+            const float4* xg4 = reinterpret_cast<const float4*>(xg);
+            const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
+            int i = lane / Q, q = lane - (lane / Q) * Q;
+#pragma unroll 8
+            for (int e = lane; e < L * Q; e += 32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(tile) + word(i) + 4 * q) = __ldg(xg4 + e);
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+        } else {
+            const int di = 32 / C, dc = 32 - di * C;
+            int i = lane / C, cc = lane - (lane / C) * C;
+#pragma unroll 4
+            for (int e = lane; e < L * C; e += 32) {
+                tile[word(i) + cc] = xg[e];
+                i += di;
+                cc += dc;
+                if (cc >= C) { cc -= C; ++i; }
+            }
+        }
+        __syncwarp();
+        // backward: thread the holes (payload: distance to the next observation / next hole of the chunk, 0 = none)
+        int first_idx = kFillNone, last_idx = -1, head = -1;
+        T last_val = T(0);
+        if (active) {
+            T* ptr = tile + word(g1 - 1) + c;
+            for (int i = g1 - 1; i >= g0; --i, ptr -= C) {
+                const T w = *ptr;
+                if (is_nan(w)) {
+                    const int d_obs = first_idx == kFillNone ? 0 : first_idx - i;
+                    const int d_hole = head < 0 ? 0 : head - i;
+                    *ptr = nan_code<T>::make(d_obs | (d_hole << kFillDist));
+                    head = i;
+                } else {
+                    if (last_idx < 0) { last_idx = i; last_val = w; }
+                    first_idx = i;
+                }
+            }
+        }
+        saw_nan |= head >= 0;
+        // nearest observation in the chunks after (position) and before (position, value) this one
+        int after = kFillNone, before = -1;
+        T before_val = T(0);
+        for (int d = 1; d < nch; ++d) {
+            const int fa = __shfl_down_sync(full, first_idx, C * d);
+            const int la = __shfl_up_sync(full, last_idx, C * d);
+            const T lv = __shfl_up_sync(full, last_val, C * d);
+            if (after == kFillNone && j + d < nch) after = fa;
+            if (before < 0 && j - d >= 0) { before = la; before_val = lv; }
+        }
+        const int series_first = __shfl_sync(full, first_idx != kFillNone ? first_idx : after, c);
+        const int series_last = __shfl_sync(full, last_idx >= 0 ? last_idx : before, c + C * (nch - 1));
+        if (active) {
+            if (series_first == kFillNone) {                // nothing observed: the zero path (linear.py:19-21)
+                T* ptr = tile + word(g0) + c;
+                for (int i = g0; i < g1; ++i, ptr += C) *ptr = T(0);
+            } else {
+                const T v_first = tile[word(series_first) + c], v_last = tile[word(series_last) + c];
+                // the ends of the series count as observations carrying the first / last value (linear.py:31-34)
+                int prev_idx = before >= 0 ? before : 0;
+                T prev_val = before >= 0 ? before_val : v_first;
+                const int far_idx = after != kFillNone ? after : L - 1;
+                const T far_val = after != kFillNone ? tile[word(after) + c] : v_last;
+                T* base = tile + word(g0) + c;              // a chunk has no padding inside
+                T lo_t = T(0), span = T(1), rise = T(0);
+                for (int i = head, visited = -2; i >= 0;) {
+                    T* ptr = base + (i - g0) * C;
+                    const int code = nan_code<T>::get(*ptr);
+                    const int d_obs = code & ((1 << kFillDist) - 1), d_hole = code >> kFillDist;
+                    if (i != visited + 1) {                 // a new gap: fetch its end points
+                        if (i > g0) {
+                            prev_idx = i - 1;
+                            prev_val = ptr[-C];
+                        }
+                        const int hi_i = d_obs ? i + d_obs : far_idx;
+                        const T hi_v = d_obs ? ptr[d_obs * C] : far_val;
+                        lo_t = time_of(prev_idx);
+                        span = E::sub(time_of(hi_i), lo_t);
+                        rise = E::sub(hi_v, prev_val);
+                    }
+                    // linear.py:60-69: x[j] = lo + ((t_j - t_lo) / (t_hi - t_lo)) * (hi - lo)
+                    *ptr = E::add(prev_val, E::mul(E::div(E::sub(time_of(i), lo_t), span), rise));
+                    visited = i;
+                    i = d_hole ? i + d_hole : -1;
+                }
+                // an imputed end point is a copy of the observation, not an interpolation
+                if (g0 == 0 && series_first > 0) tile[c] = v_first;
+                if (g1 == L && series_last < L - 1) tile[word(L - 1) + c] = v_last;
+            }
+        }
+        __syncwarp();
+        if (vec4) {
+            float4* og4 = reinterpret_cast<float4*>(og);
+            const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
+            int i = lane / Q, q = lane - (lane / Q) * Q;
+#pragma unroll 8
+            for (int e = lane; e < L * Q; e += 32) {
+                og4[e] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tile) + word(i) + 4 * q);
+                i += dq_i;
+                q += dq_q;
+                if (q >= Q) { q -= Q; ++i; }
+            }
+        } else {
+            const int di = 32 / C, dc = 32 - di * C;
+            int i = lane / C, cc = lane - (lane / C) * C;
+#pragma unroll 4
+            for (int e = lane; e < L * C; e += 32) {
+                og[e] = tile[word(i) + cc];
+                i += di;
+                cc += dc;
+                if (cc >= C) { cc -= C; ++i; }
+            }
+        }
+    }
+    if (saw_nan && flags != nullptr) atomicOr(flags, TCDE_FLAG_NAN_SEEN);
+}
+
 // misc.forward_fill (misc.py:103-126) and _prepare_rectilinear_interpolation
 // (interpolation_linear.py:87-128).  RECT = false: out has L rows; RECT = true: 2L-1 rows, row
 // 2i = held[i], row 2i+1 = held[i] except the time channel which takes held[i+1].
@@ -1336,7 +1511,8 @@ nan_flag_kernel(const T* __restrict__ x, int64_t n, int32_t* __restrict__ flags)
 // =========================================================================================
 // launchers
 // =========================================================================================
-static int g_fill_variant = 0;        // 0 = warp-per-path gap fill when it fits, 1 = one thread per series
+static int g_fill_variant = 0;        // 0 = scan / ballot warp-per-path gap fill when they fit, 1 = one thread per
+                                      // series, 2 = never the scan kernel
 static int g_natural_variant = 0;     // 0 = warp per path / windowed CTA sweeps when they fit, 1 = one thread per
                                       // series, 2 = never the warp-per-path kernel
 
@@ -1500,13 +1676,42 @@ extern "C" int tcde_hermite_bdiff_coeffs(const void* x, const void* t, void* coe
 }
 
 extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t n_paths, int64_t length,
-                                int64_t channels, int dtype, void* stream) {
+                                int64_t channels, int dtype, int32_t* flags, void* stream) {
     int rc = check_shape(x, out, n_paths, length, channels, dtype);
     if (rc != TCDE_OK) return rc;
     const int64_t n_series = n_paths * channels;
     if (n_series == 0) return TCDE_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int L = (int)length, C = (int)channels;
+    if (C <= 32 && L < kFillNone && g_fill_variant == 0) {
+        // scan kernel: lane = (channel, chunk of positions), tile in the global layout
+        const size_t elem = (dtype == TCDE_F32) ? 4 : 8;
+        const int n_chunks = 32 / C;
+        int lgG = 0;
+        while ((1 << lgG) * n_chunks < L) ++lgG;
+        const int G = 1 << lgG;
+        const int nct = (L + G - 1) / G;
+        const int bank_words = (int)(128 / elem);
+        const int padw = (int)((((int64_t)C - (int64_t)G * C) % bank_words + bank_words) % bank_words);
+        const int tile_words = (L * C + nct * padw + 3) & ~3;
+        const size_t smem = (t ? (size_t)((L + 3) & ~3) * elem : 0) + (size_t)(kThreads / 32) * tile_words * elem;
+        if (smem <= 100 * 1024 && lgG < kFillDist) {          // hole-list distances are 11-bit
+            const void* kern = (dtype == TCDE_F32)
+                ? (t ? (const void*)linear_fill_scan_kernel<float, false> : (const void*)linear_fill_scan_kernel<float, true>)
+                : (t ? (const void*)linear_fill_scan_kernel<double, false> : (const void*)linear_fill_scan_kernel<double, true>);
+            TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = persistent_grid(kern, kThreads, smem, (n_paths + kThreads / 32 - 1) / (kThreads / 32));
+            const int Li = L, Ci = C;
+            void* args[] = {(void*)&x, (void*)&t, (void*)&out, (void*)&n_paths, (void*)&Li, (void*)&Ci, (void*)&lgG,
+                            (void*)&padw, (void*)&tile_words, (void*)&flags};
+            TCDE_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, smem, s));
+            return TCDE_OK;
+        }
+    }
+    if (flags != nullptr) {               // the other kernels do not report: a separate pass over x
+        rc = tcde_nan_flag(x, n_series * L, dtype, flags, stream);
+        if (rc != TCDE_OK) return rc;
+    }
     {
         // warp-per-path kernel when a path fits a warp's shared-memory tile
         const int Lp = ((L + 31) / 32) * 32 + 1;
