@@ -191,3 +191,100 @@ def test_adjoint_gradients_match_backprop_through_the_solver(method, kw):
     tol = 2e-3 if method == "rk4" else 1e-5
     for a, b in zip(*grads):
         assert torch.allclose(a, b, rtol=tol, atol=tol * float(b.abs().max()))
+
+
+def _vjp_reference(control, kind, weight, bias, z, a, index, frac, scale):
+    """fp64 autograd statement of what tcde_vector_field_linear_vjp returns."""
+    w = weight.double().clone().requires_grad_(True)
+    b = bias.double().clone().requires_grad_(True)
+    zz = z.double().clone().requires_grad_(True)
+    c = control.double()
+    channels = b.numel() // zz.size(-1)
+    if kind == "cubic":
+        row = c[:, index]
+        dx = row[:, channels:2 * channels] + (row[:, 2 * channels:3 * channels] + row[:, 3 * channels:] * frac) * frac
+    else:
+        dx = c[:, index]
+    f = (torch.nn.functional.linear(zz, w, b).view(zz.size(0), zz.size(1), channels) @ dx.unsqueeze(-1)).squeeze(-1)
+    gz, gw, gb = torch.autograd.grad(f, (zz, w, b), a.double() * scale)
+    return f.detach(), gz, gw, gb
+
+
+@pytest.mark.parametrize("n_paths", [1, 63, 64, 65, 1000, 20011])
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+def test_fused_adjoint_stage_against_autograd(n_paths, kind):
+    """tcde_vector_field_linear_vjp (hidden 32, channels 8, fp32): field value, a^T df/dz and the parameter
+    gradients (accumulated onto what the buffers already hold) vs fp64 autograd of the same expression."""
+    from torchcde_b200 import _lib
+    gen = torch.Generator().manual_seed(n_paths)
+    hidden, channels, n_rows = 32, 8, 5
+    width = 4 * channels if kind == "cubic" else channels
+    control = torch.randn(n_paths, n_rows, width, generator=gen).to(DEV)
+    weight = (torch.randn(hidden * channels, hidden, generator=gen) / math.sqrt(hidden)).to(DEV)
+    bias = torch.randn(hidden * channels, generator=gen).to(DEV)
+    z = torch.randn(n_paths, hidden, generator=gen).to(DEV)
+    a = torch.randn(n_paths, hidden, generator=gen).to(DEV)
+    index, frac, scale = 3, 0.37, -0.75
+    f = torch.empty_like(z)
+    vz = torch.empty_like(z)
+    gw0 = torch.randn(hidden * channels, hidden, generator=gen).to(DEV)
+    gb0 = torch.randn(hidden * channels, generator=gen).to(DEV)
+    gw, gb = gw0.clone(), gb0.clone()
+    nbytes = _lib.load().tcde_vector_field_linear_vjp_scratch_bytes(n_paths, channels, hidden)
+    assert nbytes > 0
+    scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=DEV)
+    code = _lib.dtype_code(z.dtype)
+    _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), _lib.CONTROL_CUBIC if kind == "cubic" else
+              _lib.CONTROL_LINEAR, n_rows, _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(z), _lib.ptr(a), _lib.ptr(f),
+              _lib.ptr(vz), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(scratch), n_paths, channels, hidden, index, frac, scale,
+              code, _lib.stream_of(z))
+    wf, wz, ww, wb = _vjp_reference(control, kind, weight, bias, z, a, index, frac, scale)
+
+    def close(got, want, tol=2e-5):
+        return float((got.double() - want).abs().max()) <= tol * max(1.0, float(want.abs().max()))
+
+    assert close(f, wf) and close(vz, wz)
+    assert close(gw - gw0, ww, 5e-5) and close(gb - gb0, wb, 5e-5)
+    # the forward-only entry point returns the same field
+    f2 = torch.empty_like(z)
+    _lib.call("tcde_vector_field_linear", _lib.ptr(control), _lib.CONTROL_CUBIC if kind == "cubic" else
+              _lib.CONTROL_LINEAR, n_rows, _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(z), _lib.ptr(f2), n_paths, channels,
+              hidden, index, frac, code, _lib.stream_of(z))
+    assert close(f, f2.double(), 1e-6)
+    with pytest.raises(NotImplementedError):
+        _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), _lib.CONTROL_LINEAR, n_rows, _lib.ptr(weight),
+                  _lib.ptr(bias), _lib.ptr(z), _lib.ptr(a), _lib.ptr(f), _lib.ptr(vz), None, None, _lib.ptr(scratch),
+                  n_paths, 4, 16, index, frac, scale, code, _lib.stream_of(z))
+
+
+@pytest.mark.parametrize("method,kw", [("rk4", {"options": {"step_size": 0.25}}), ("midpoint", {"options": {"step_size": 0.25}}),
+                                       ("dopri5", {})])
+def test_fused_adjoint_matches_the_autograd_adjoint(method, kw, monkeypatch):
+    """cdeint(adjoint=True) at the flagship field shape (hidden 32, channels 8, fp32): the backward solve that
+    uses the fused stage kernel gives the gradients of the one that uses autograd (same algorithm, same steps)."""
+    from torchcde_b200 import solver
+    x, z0, func = _problem(37, 12, 8, 32, seed=5)
+    func = func.to(DEV)
+    with torch.no_grad():
+        X = cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x.to(DEV)))
+    t = torch.tensor([0.0, 4.5, 11.0])
+    grads, used = [], []
+    real = solver._kernel_vjp
+    for fused in (True, False):
+        def probe(*args, _fused=fused, **kwargs):
+            stage = real(*args, **kwargs) if _fused else None
+            used.append(stage is not None)
+            return stage
+        monkeypatch.setattr(solver, "_kernel_vjp", probe)
+        zz = z0.to(DEV).clone().requires_grad_(True)
+        func.zero_grad()
+        out = cde.cdeint(X, func, zz, t, adjoint=True, method=method, rtol=1e-5, atol=1e-7, **kw)
+        (out[:, 1].pow(2).sum() + out[:, 2].sum()).backward()
+        grads.append((zz.grad.clone(), func.linear.weight.grad.clone(), func.linear.bias.grad.clone()))
+    assert used == [True, False]
+    # fixed steps: the two backward solves do the same arithmetic up to summation order.  dopri5: its error norm is
+    # dominated by the parameter-gradient components (|dL/dW| ~ 100 vs |a| ~ 1), so rtol=1e-5 on the whole state
+    # leaves ~1e-2 relative freedom on the small components and the two runs may pick different steps
+    rtol, scale = (5e-2, 5e-3) if method == "dopri5" else (2e-3, 2e-4)
+    for got, want in zip(*grads):
+        assert torch.allclose(got, want, rtol=rtol, atol=scale * float(want.abs().max()))

@@ -216,8 +216,8 @@ class _Adjoint(torch.autograd.Function):
     with the same solver family, evaluating the vector field under autograd for its VJPs."""
 
     @staticmethod
-    def forward(ctx, forward_solve, vf, times, solve_aug, n_params, y0, *params):
-        ctx.vf, ctx.times, ctx.solve_aug = vf, times, solve_aug
+    def forward(ctx, forward_solve, vf, times, solve_aug, fused_vjp, y0, *params):
+        ctx.vf, ctx.times, ctx.solve_aug, ctx.fused_vjp = vf, times, solve_aug, fused_vjp
         with torch.no_grad():
             ys = forward_solve(y0)
         ctx.save_for_backward(ys, *params)
@@ -243,6 +243,10 @@ class _Adjoint(torch.autograd.Function):
 
         def aug_field(t, flat):
             y, a_y, *_ = unpack(flat)
+            if ctx.fused_vjp is not None:
+                # one launch: the field and its three vector-Jacobian products with the cotangent -a_y
+                f, vjp_y, vjp_p = ctx.fused_vjp(t, y, a_y, -1.0)
+                return pack([f, vjp_y] + vjp_p)
             with torch.enable_grad():
                 y_ = y.detach().requires_grad_(True)
                 f = vf(t, y_)
@@ -263,7 +267,11 @@ class _Adjoint(torch.autograd.Function):
         return (None, None, None, None, None, a_y, *a_p)
 
 
-def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params):
-    """``forward_solve(y0) -> ys`` (time first); ``vf(t_float, y)`` differentiable in y and ``params``."""
+def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params, fused_vjp=None):
+    """``forward_solve(y0) -> ys`` (time first); ``vf(t_float, y)`` differentiable in y and ``params``.
+
+    ``fused_vjp(params)``, if given, returns ``None`` or a callable ``(t, y, a, scale) -> (f, scale * a^T df/dy,
+    [scale * a^T df/dp for p in params])`` that replaces autograd in the backward solve."""
     params = tuple(p for p in params if p.requires_grad)
-    return _Adjoint.apply(forward_solve, vf, times, solve_aug, len(params), y0, *params)
+    stage = fused_vjp(params) if fused_vjp is not None else None
+    return _Adjoint.apply(forward_solve, vf, times, solve_aug, stage, y0, *params)

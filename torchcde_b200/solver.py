@@ -297,6 +297,53 @@ def _kernel_field(X, weight, bias, z0):
     return field
 
 
+def _kernel_vjp(X, weight, bias, z0, params):
+    """The adjoint stage of the linear field as ONE launch of ``tcde_vector_field_linear_vjp``:
+    ``(t, y, a, scale) -> (f, scale * a^T df/dy, [scale * a^T df/dp for p in params])``, or ``None`` when the
+    kernel is not built for this problem (then autograd serves the backward solve)."""
+    kind, _, channels, n_rows = _control_signature(X)
+    hidden = z0.size(-1)
+    roles = []
+    for p in params:
+        if p is weight:
+            roles.append("w")
+        elif bias is not None and p is bias:
+            roles.append("b")
+        else:
+            return None                       # a parameter that is not the linear map: autograd knows how
+    if z0.dtype != torch.float32 or weight.dtype != torch.float32:
+        return None
+    n_paths = z0.numel() // hidden
+    scratch_bytes = _lib.load().tcde_vector_field_linear_vjp_scratch_bytes(n_paths, channels, hidden)
+    if scratch_bytes < 0:
+        return None
+    code = _lib.dtype_code(z0.dtype)
+    control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+    control = control.detach().reshape(-1, control.size(-2), control.size(-1)).contiguous()
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous() if bias is not None else torch.zeros(hidden * channels, dtype=z0.dtype,
+                                                                        device=z0.device)
+    scratch = torch.empty(max(scratch_bytes // 4, 4), dtype=torch.float32, device=z0.device)
+    where = _host_locator(X, z0.dtype)
+
+    def stage(t, y, a, scale):
+        index, frac = where(t)
+        yf = y.reshape(-1, hidden).contiguous()
+        af = a.reshape(-1, hidden).contiguous()
+        f = torch.empty_like(yf)
+        vjp_y = torch.empty_like(yf)
+        gw = torch.zeros_like(w) if "w" in roles else None
+        gb = torch.zeros_like(b) if "b" in roles else None
+        with torch.cuda.device(y.device):
+            _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), kind, n_rows, _lib.ptr(w), _lib.ptr(b),
+                      _lib.ptr(yf), _lib.ptr(af), _lib.ptr(f), _lib.ptr(vjp_y), _lib.ptr(gw), _lib.ptr(gb),
+                      _lib.ptr(scratch), yf.size(0), channels, hidden, index, float(frac), float(scale), code,
+                      _lib.stream_of(yf))
+        return f.view_as(y), vjp_y.view_as(y), [gw if r == "w" else gb for r in roles]
+
+    return stage
+
+
 def _torch_field(X, func, is_prod, known_control, z0):
     """The reference's ``_VectorField.forward`` (solver.py:117-135) as differentiable torch ops."""
     where = _host_locator(X, z0.dtype) if known_control else None
@@ -477,7 +524,13 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                 return adaptive.odeint_fixed(f, v, ts, a_method, a_options.get("step_size", None))
             return adaptive.odeint_dopri5(f, v, ts, a_rtol, a_atol)[0]
 
-        ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params)
+        def fused_vjp(params):
+            if field_params is None or flipped:          # decreasing t: autograd (rare; keeps one code path)
+                return None
+            return _kernel_vjp(X, field_params[0], field_params[1], z0, params)
+
+        ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params,
+                                         fused_vjp)
         return _time_first_to_reference_layout(ys)
 
     # adjoint=False: backpropagate through the solver's own operations, like torchdiffeq.odeint
