@@ -129,10 +129,12 @@ TCDE_API int tcde_vector_field_linear(const void* control, int control_kind, int
 /* The same evaluation together with its vector-Jacobian products -- one stage of torchdiffeq's
  * odeint_adjoint (the reference's default, solver.py:144 and :226-227), which the stock stack gets
  * from autograd:
- *   f_out[p][h]        = field as above
- *   vjp_z_out[p][k]    = scale * sum_h a[p][h] d f[p][h] / d z[p][k]
- *   grad_weight[n][k] += scale * sum_p sum_h a[p][h] d f[p][h] / d weight[n][k]      (n = h*C + c)
- *   grad_bias[n]      += scale * sum_p sum_h a[p][h] d f[p][h] / d bias[n]
+ *   f_out[p][h]        = f_scale * field as above
+ *   vjp_z_out[p][k]    = vjp_scale * sum_h a[p][h] d f[p][h] / d z[p][k]
+ *   grad_weight[n][k] += grad_scale * sum_p sum_h a[p][h] d f[p][h] / d weight[n][k]      (n = h*C + c)
+ *   grad_bias[n]      += grad_scale * sum_p sum_h a[p][h] d f[p][h] / d bias[n]
+ * (the scales carry the signs of the reversed-time solve and the Runge-Kutta weight of the stage, so a
+ * fixed-step backward solve accumulates the parameter gradients in place).
  * grad_weight / grad_bias may be NULL.  scratch: device buffer of
  * tcde_vector_field_linear_vjp_scratch_bytes(...) bytes (per-CTA partial sums; -1 = shape not built).
  * Built for fp32, hidden = 32, channels = 8 (TCDE_ERR_UNSUPPORTED otherwise: the caller keeps autograd). */
@@ -140,7 +142,8 @@ TCDE_API int64_t tcde_vector_field_linear_vjp_scratch_bytes(int64_t n_paths, int
 TCDE_API int tcde_vector_field_linear_vjp(const void* control, int control_kind, int64_t n_rows, const void* weight,
                                  const void* bias, const void* z, const void* a, void* f_out, void* vjp_z_out,
                                  void* grad_weight, void* grad_bias, void* scratch, int64_t n_paths, int64_t channels,
-                                 int64_t hidden, int32_t index, double frac, double scale, int dtype, void* stream);
+                                 int64_t hidden, int32_t index, double frac, double f_scale, double vjp_scale,
+                                 double grad_scale, int dtype, void* stream);
 
 /* The fused fixed-step solve: everything torchdiffeq's fixed-grid odeint does for
  * cdeint(X, func, z0, t, method in {euler, midpoint, rk4}, options={step_size})

@@ -236,8 +236,8 @@ def test_fused_adjoint_stage_against_autograd(n_paths, kind):
     code = _lib.dtype_code(z.dtype)
     _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), _lib.CONTROL_CUBIC if kind == "cubic" else
               _lib.CONTROL_LINEAR, n_rows, _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(z), _lib.ptr(a), _lib.ptr(f),
-              _lib.ptr(vz), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(scratch), n_paths, channels, hidden, index, frac, scale,
-              code, _lib.stream_of(z))
+              _lib.ptr(vz), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(scratch), n_paths, channels, hidden, index, frac, 1.0,
+              scale, scale, code, _lib.stream_of(z))
     wf, wz, ww, wb = _vjp_reference(control, kind, weight, bias, z, a, index, frac, scale)
 
     def close(got, want, tol=2e-5):
@@ -254,7 +254,7 @@ def test_fused_adjoint_stage_against_autograd(n_paths, kind):
     with pytest.raises(NotImplementedError):
         _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), _lib.CONTROL_LINEAR, n_rows, _lib.ptr(weight),
                   _lib.ptr(bias), _lib.ptr(z), _lib.ptr(a), _lib.ptr(f), _lib.ptr(vz), None, None, _lib.ptr(scratch),
-                  n_paths, 4, 16, index, frac, scale, code, _lib.stream_of(z))
+                  n_paths, 4, 16, index, frac, 1.0, scale, scale, code, _lib.stream_of(z))
 
 
 @pytest.mark.parametrize("method,kw", [("rk4", {"options": {"step_size": 0.25}}), ("midpoint", {"options": {"step_size": 0.25}}),

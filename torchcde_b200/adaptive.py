@@ -216,8 +216,8 @@ class _Adjoint(torch.autograd.Function):
     with the same solver family, evaluating the vector field under autograd for its VJPs."""
 
     @staticmethod
-    def forward(ctx, forward_solve, vf, times, solve_aug, fused_vjp, y0, *params):
-        ctx.vf, ctx.times, ctx.solve_aug, ctx.fused_vjp = vf, times, solve_aug, fused_vjp
+    def forward(ctx, forward_solve, vf, times, solve_aug, fused_vjp, fixed_spec, y0, *params):
+        ctx.vf, ctx.times, ctx.solve_aug, ctx.fused_vjp, ctx.fixed_spec = vf, times, solve_aug, fused_vjp, fixed_spec
         with torch.no_grad():
             ys = forward_solve(y0)
         ctx.save_for_backward(ys, *params)
@@ -228,6 +228,10 @@ class _Adjoint(torch.autograd.Function):
         ys, *params = ctx.saved_tensors
         vf, times = ctx.vf, ctx.times
         params = tuple(params)
+        if ctx.fused_vjp is not None and ctx.fixed_spec is not None:
+            with torch.no_grad():
+                a_y, a_p = _fused_fixed_backward(ctx.fused_vjp, times, ys, grad_ys, *ctx.fixed_spec)
+            return (None, None, None, None, None, None, a_y, *a_p)
         shapes = [ys[0].shape, ys[0].shape] + [p.shape for p in params]
         sizes = [s.numel() for s in shapes]
 
@@ -264,14 +268,91 @@ class _Adjoint(torch.autograd.Function):
                 flat1 = ctx.solve_aug(lambda s, v: -aug_field(-s, v), flat0, [-times[i], -times[i - 1]])[-1]
                 _, a_y, *a_p = [x.clone() for x in unpack(flat1)]
                 a_y = a_y + grad_ys[i - 1]
-        return (None, None, None, None, None, a_y, *a_p)
+        return (None, None, None, None, None, None, a_y, *a_p)
 
 
-def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params, fused_vjp=None):
+def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
+    """The backward solve of ``_Adjoint`` for a fixed-step method when the fused adjoint stage kernel serves the
+    field: same grid, same stage times and the same Runge-Kutta combinations as ``odeint_fixed`` on the packed
+    state, but (z, a) stay one (2, ..., H) tensor that the kernel reads and writes directly, and the parameter
+    gradients -- whose slopes do not depend on themselves -- are accumulated in place by the kernel with the
+    stage's weight, instead of being carried through ``torch.cat`` as 8,448 extra state components."""
+    import math
+    grads = stage.new_grads()
+    gw = next((g for g, r in zip(grads, stage.roles) if r == "w"), None)
+    gb = next((g for g, r in zip(grads, stage.roles) if r == "b"), None)
+    shape = ys[0].shape
+    U = torch.empty((2,) + tuple(shape), dtype=ys.dtype, device=ys.device)
+    V = torch.empty_like(U)
+    tmp = torch.empty_like(U)
+    K = [torch.empty_like(U) for _ in range(4)]
+    a_y = grad_ys[-1].clone()
+
+    def field(idx, frac, state, out, weight):
+        # d(z, a)/ds = (-f, +a^T df/dz), d(grad)/ds = +a^T df/dp  (s = -t), the latter times the stage weight
+        if weight == 0.0:
+            stage.launch(idx, frac, state[0], state[1], out[0], out[1], None, None, -1.0, 1.0, 0.0)
+        else:
+            stage.launch(idx, frac, state[0], state[1], out[0], out[1], gw, gb, -1.0, 1.0, weight)
+
+    for i in range(len(times) - 1, 0, -1):
+        s0, s_end = -times[i], -times[i - 1]
+        if step_size is None:
+            grid = [s0, s_end]
+        else:
+            n = int(math.ceil((s_end - s0) / step_size + 1))
+            grid = [s0 + j * step_size for j in range(n)]
+            grid[-1] = s_end
+        stage_times = []
+        for lo, hi in zip(grid[:-1], grid[1:]):
+            ds = hi - lo
+            if method == "rk4":
+                stage_times += [lo, lo + ds / 3, lo + ds * 2 / 3, hi]
+            elif method == "midpoint":
+                stage_times += [lo, lo + ds / 2]
+            else:
+                stage_times += [lo]
+        index, frac = stage.locate_many([-s for s in stage_times])
+        U[0].copy_(ys[i])
+        U[1].copy_(a_y)
+        e = 0
+        for lo, hi in zip(grid[:-1], grid[1:]):
+            ds = hi - lo
+            if method == "rk4":
+                field(index[e], frac[e], U, K[0], ds * 0.125)
+                torch.add(U, K[0], alpha=ds / 3, out=V)
+                field(index[e + 1], frac[e + 1], V, K[1], ds * 0.375)
+                torch.add(K[1], K[0], alpha=-1.0 / 3, out=tmp)
+                torch.add(U, tmp, alpha=ds, out=V)
+                field(index[e + 2], frac[e + 2], V, K[2], ds * 0.375)
+                torch.sub(K[0], K[1], out=tmp)
+                tmp.add_(K[2])
+                torch.add(U, tmp, alpha=ds, out=V)
+                field(index[e + 3], frac[e + 3], V, K[3], ds * 0.125)
+                torch.add(K[1], K[2], out=tmp)
+                torch.add(K[0], tmp, alpha=3.0, out=tmp)
+                tmp.add_(K[3])
+                U.add_(tmp, alpha=ds * 0.125)
+                e += 4
+            elif method == "midpoint":
+                field(index[e], frac[e], U, K[0], 0.0)
+                torch.add(U, K[0], alpha=ds / 2, out=V)
+                field(index[e + 1], frac[e + 1], V, K[1], ds)
+                U.add_(K[1], alpha=ds)
+                e += 2
+            else:
+                field(index[e], frac[e], U, K[0], ds)
+                U.add_(K[0], alpha=ds)
+                e += 1
+        a_y = U[1] + grad_ys[i - 1]
+    return a_y, grads
+
+
+def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params, fused_vjp=None, fixed_spec=None):
     """``forward_solve(y0) -> ys`` (time first); ``vf(t_float, y)`` differentiable in y and ``params``.
 
     ``fused_vjp(params)``, if given, returns ``None`` or a callable ``(t, y, a, scale) -> (f, scale * a^T df/dy,
     [scale * a^T df/dp for p in params])`` that replaces autograd in the backward solve."""
     params = tuple(p for p in params if p.requires_grad)
     stage = fused_vjp(params) if fused_vjp is not None else None
-    return _Adjoint.apply(forward_solve, vf, times, solve_aug, stage, y0, *params)
+    return _Adjoint.apply(forward_solve, vf, times, solve_aug, stage, fixed_spec, y0, *params)

@@ -3,10 +3,11 @@
 //
 // torchdiffeq's odeint_adjoint (the reference's default, solver.py:144 / 226-227) integrates the
 // augmented state (z, a, dL/dW, dL/db) backwards in time; every stage of that solve needs
-//     f[p][h]      = sum_c (b[hC+c] + sum_k W[hC+c][k] z[p][k]) dX[p][c]
-//     vz[p][k]     = s * sum_h a[p][h] sum_c W[hC+c][k] dX[p][c]                  (a^T df/dz)
-//     gW[hC+c][k] += s * sum_p a[p][h] dX[p][c] z[p][k]                            (a^T df/dW)
-//     gb[hC+c]    += s * sum_p a[p][h] dX[p][c]                                    (a^T df/db)
+//     f[p][h]      = sf * sum_c (b[hC+c] + sum_k W[hC+c][k] z[p][k]) dX[p][c]
+//     vz[p][k]     = sv * sum_h a[p][h] sum_c W[hC+c][k] dX[p][c]                 (a^T df/dz)
+//     gW[hC+c][k] += sg * sum_p a[p][h] dX[p][c] z[p][k]                           (a^T df/dW)
+//     gb[hC+c]    += sg * sum_p a[p][h] dX[p][c]                                   (a^T df/db)
+// (sf, sv: the signs of the reversed-time solve; sg: sign times the Runge-Kutta weight of the stage)
 // which the generic path gets from autograd (~40 launches and a 64 MB intermediate per stage).
 // Here a persistent CTA walks tiles of 64 paths.  f and vz are the same register-tiled product as
 // the forward CUDA-core kernel (solve_simt.cu), once with (z, W) and once with (a, W regrouped as
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 field_vjp_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ weight,
                  const float* __restrict__ bias, const float* __restrict__ z, const float* __restrict__ a,
                  float* __restrict__ f_out, float* __restrict__ vz_out, float* __restrict__ scratch, int64_t n_paths,
-                 int index, float frac, float scale) {
+                 int index, float frac, float f_scale, float vjp_scale) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using E = exact<float>;
     float* smem = reinterpret_cast<float*>(smem_raw);
@@ -160,7 +161,7 @@ field_vjp_kernel(const float* __restrict__ control, int control_kind, int64_t n_
                 }
             }
             float* dst = (which == 0) ? f_out : vz_out;
-            const float mult = (which == 0) ? 1.f : scale;
+            const float mult = (which == 0) ? f_scale : vjp_scale;
 #pragma unroll
             for (int s = 0; s < ST; ++s) {
                 const int64_t p = path0 + lp0 + s;
@@ -234,7 +235,8 @@ extern "C" int tcde_vector_field_linear_vjp(const void* control, int control_kin
                                             const void* bias, const void* z, const void* a, void* f_out,
                                             void* vjp_z_out, void* grad_weight, void* grad_bias, void* scratch,
                                             int64_t n_paths, int64_t channels, int64_t hidden, int32_t index,
-                                            double frac, double scale, int dtype, void* stream) {
+                                            double frac, double f_scale, double vjp_scale, double grad_scale,
+                                            int dtype, void* stream) {
     TCDE_CHECK_ARG(control && weight && bias && z && a && f_out && vjp_z_out && scratch, "null data pointer");
     TCDE_CHECK_ARG(n_paths >= 0 && channels >= 1 && hidden >= 1 && n_rows >= 1, "bad sizes");
     TCDE_CHECK_ARG(index >= 0 && index < n_rows, "index=%d outside [0, %lld)", index, (long long)n_rows);
@@ -253,10 +255,10 @@ extern "C" int tcde_vector_field_linear_vjp(const void* control, int control_kin
     vjp::field_vjp_kernel<<<grid, vjp::kThreads, smem, s>>>(
         (const float*)control, control_kind, n_rows, (const float*)weight, (const float*)bias, (const float*)z,
         (const float*)a, (float*)f_out, (float*)vjp_z_out, (float*)scratch, n_paths, (int)index, (float)frac,
-        (float)scale);
+        (float)f_scale, (float)vjp_scale);
     TCDE_CHECK_CUDA(cudaGetLastError());
     if (grad_weight || grad_bias) {
-        vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 255) / 256, 256, 0, s>>>((const float*)scratch, grid, (float)scale,
+        vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 255) / 256, 256, 0, s>>>((const float*)scratch, grid, (float)grad_scale,
                                                                                 (float*)grad_weight, (float*)grad_bias);
         TCDE_CHECK_CUDA(cudaGetLastError());
     }

@@ -325,6 +325,14 @@ def _kernel_vjp(X, weight, bias, z0, params):
                                                                         device=z0.device)
     scratch = torch.empty(max(scratch_bytes // 4, 4), dtype=torch.float32, device=z0.device)
     where = _host_locator(X, z0.dtype)
+    knots = _schedule_knots(X)
+
+    def launch(index, frac, y, a, f_out, vjp_out, gw, gb, f_scale, vjp_scale, grad_scale):
+        with torch.cuda.device(y.device):
+            _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), kind, n_rows, _lib.ptr(w), _lib.ptr(b),
+                      _lib.ptr(y), _lib.ptr(a), _lib.ptr(f_out), _lib.ptr(vjp_out), _lib.ptr(gw), _lib.ptr(gb),
+                      _lib.ptr(scratch), y.numel() // hidden, channels, hidden, index, float(frac), float(f_scale),
+                      float(vjp_scale), float(grad_scale), code, _lib.stream_of(y))
 
     def stage(t, y, a, scale):
         index, frac = where(t)
@@ -334,13 +342,19 @@ def _kernel_vjp(X, weight, bias, z0, params):
         vjp_y = torch.empty_like(yf)
         gw = torch.zeros_like(w) if "w" in roles else None
         gb = torch.zeros_like(b) if "b" in roles else None
-        with torch.cuda.device(y.device):
-            _lib.call("tcde_vector_field_linear_vjp", _lib.ptr(control), kind, n_rows, _lib.ptr(w), _lib.ptr(b),
-                      _lib.ptr(yf), _lib.ptr(af), _lib.ptr(f), _lib.ptr(vjp_y), _lib.ptr(gw), _lib.ptr(gb),
-                      _lib.ptr(scratch), yf.size(0), channels, hidden, index, float(frac), float(scale), code,
-                      _lib.stream_of(yf))
+        launch(index, frac, yf, af, f, vjp_y, gw, gb, 1.0, scale, scale)
         return f.view_as(y), vjp_y.view_as(y), [gw if r == "w" else gb for r in roles]
 
+    def locate_many(times):
+        """Interval index / fraction of a list of stage times, with the casts of ``_host_locator``, in one go."""
+        tt = torch.tensor(times, dtype=torch.float64).to(z0.dtype)
+        frac, index = locate(knots, tt.to(knots.dtype), n_rows)
+        return index.tolist(), frac.tolist()
+
+    stage.launch = launch
+    stage.locate_many = locate_many
+    stage.roles = roles
+    stage.new_grads = lambda: [torch.zeros_like(w) if r == "w" else torch.zeros_like(b) for r in roles]
     return stage
 
 
@@ -529,8 +543,9 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                 return None
             return _kernel_vjp(X, field_params[0], field_params[1], z0, params)
 
+        fixed_spec = (a_method, a_options.get("step_size", None)) if a_method in FIXED_METHODS else None
         ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params,
-                                         fused_vjp)
+                                         fused_vjp, fixed_spec)
         return _time_first_to_reference_layout(ys)
 
     # adjoint=False: backpropagate through the solver's own operations, like torchdiffeq.odeint
