@@ -376,6 +376,21 @@ def run_gpu_arm(args):
                 if remark:
                     extra[name]["note"] = remark
             del xn, rows
+            # training step at the same shapes: cdeint(adjoint=True) forward + backward (fused adjoint stage kernel)
+            try:
+                def train_step():
+                    zz = z0.clone().requires_grad_(True)
+                    func.zero_grad()
+                    with torch.enable_grad():
+                        res = cde.cdeint(X, func, zz, t, adjoint=True, method="rk4", options=options)
+                        res[:, -1].sum().backward()
+
+                t_ms = time_loop(train_step, 2, 1, device) / 2
+                extra["cdeint_rk4_forward_plus_adjoint_backward"] = {
+                    "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "fp32 fma",
+                    "note": "1,020 launches of tcde_vector_field_linear_vjp drive the backward solve; not the headline"}
+            except Exception as exc:      # never lose the headline line over the extra
+                extra["cdeint_rk4_forward_plus_adjoint_backward"] = {"error": repr(exc)}
 
     if rank != 0:
         if dist is not None:
