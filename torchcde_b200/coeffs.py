@@ -3,7 +3,7 @@
 Same names, arguments, shapes, exception types and messages as the reference builders
 (interpolation_linear.py:131-171, interpolation_hermite_cubic_bdiff.py:23-44,
 interpolation_cubic.py:173-265, misc.py:70-126); the arithmetic runs in the CUDA kernels of
-``csrc/builders.cu`` through the C ABI.  CUDA tensors only; float32 / float64.
+``csrc/hermite.cu``, ``natural.cu`` and ``fill.cu`` through the C ABI.  CUDA tensors only; float32 / float64.
 """
 import math
 import warnings
