@@ -171,6 +171,20 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
                              double sign, int dtype, void* stream);
 
+/* Elementwise pieces of the adaptive driver that stands in for torchdiffeq's dopri5 (the reference's default
+ * method, solver.py:226-227): out[i] = base[i] + sum_j coefs[j] * terms[j][i]  (base may be NULL; at most 7
+ * terms; `terms` / `coefs` are HOST arrays of device pointers / doubles, read at launch). */
+TCDE_API int tcde_linear_combination(void* out, const void* base, const void* const* terms, const double* coefs,
+                            int n_terms, int64_t n, int dtype, void* stream);
+
+/* The error ratio of one attempted step (rk_common._compute_error_ratio, restated): with
+ * err = sum_j coefs[j] * terms[j] and tol = atol + rtol * max(|y0|, |y1|), partials[c] receives the sum over
+ * CTA c's elements of (err / tol)^2; the RMS norm is sqrt(sum(partials) / n).  partials: device double
+ * [tcde_error_ratio_partials(n)]. */
+TCDE_API int64_t tcde_error_ratio_partials(int64_t n);
+TCDE_API int tcde_error_ratio_sumsq(const void* y0, const void* y1, const void* const* terms, const double* coefs,
+                           int n_terms, double atol, double rtol, int64_t n, int dtype, void* partials, void* stream);
+
 /* Profiling aid: a device buffer of 64 x 8 int64 that the tensor-core solve kernel (variant 2)
  * fills with clock64 stamps of CTA 0 / tile 0 for its first 64 stages; NULL (default) disables. */
 TCDE_API int tcde_set_trace_buffer(void* device_buffer);

@@ -288,3 +288,31 @@ def test_fused_adjoint_matches_the_autograd_adjoint(method, kw, monkeypatch):
     rtol, scale = (5e-2, 5e-3) if method == "dopri5" else (2e-3, 2e-4)
     for got, want in zip(*grads):
         assert torch.allclose(got, want, rtol=rtol, atol=scale * float(want.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(1,), (257, 3), (100003,), (8, 33, 32)])
+def test_stepper_kernels_against_torch(dtype, shape):
+    """tcde_linear_combination / tcde_error_ratio_sumsq (the elementwise part of a dopri5 attempt) vs torch."""
+    from torchcde_b200 import adaptive
+    gen = torch.Generator().manual_seed(len(shape))
+    ks = [torch.randn(shape, generator=gen, dtype=torch.float64).to(dtype).to(DEV) for _ in range(7)]
+    y0 = torch.randn(shape, generator=gen, dtype=torch.float64).to(dtype).to(DEV)
+    weights = (0.3, 0.0, -1.25, 2.0, 0.5, -0.75, 0.125)
+    dt = 0.37
+    tol = 1e-5 if dtype == torch.float32 else 1e-13
+    for base in (y0, None):
+        with torch.no_grad():
+            got = adaptive._combine(base, ks, weights, dt)
+        want = sum(k.double() * (w * dt) for k, w in zip(ks, weights)) + (0 if base is None else base.double())
+        assert got.dtype == dtype and torch.allclose(got.double(), want, rtol=tol, atol=tol)
+    y1 = y0 + 0.1 * ks[0]
+    with torch.no_grad():
+        got = adaptive._error_ratio(y0, y1, ks, weights, dt, 1e-6, 1e-4, adaptive._rms)
+    err = sum(k.double() * (w * dt) for k, w in zip(ks, weights))
+    want = float((err / (1e-6 + 1e-4 * torch.max(y0.double().abs(), y1.double().abs()))).pow(2).mean().sqrt())
+    assert abs(got - want) <= 1e-4 * want
+    # under autograd the torch operators are kept (adjoint=False differentiates through the solver)
+    yg = y0.clone().requires_grad_(True)
+    out = adaptive._combine(yg, ks, weights, dt)
+    assert out.requires_grad

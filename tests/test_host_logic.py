@@ -128,3 +128,36 @@ def test_linear_field_recognition():
     assert solver.linear_field_of(WithTanh(), z0, 2, t0) is None
     assert solver.linear_field_of(Transposed(), z0, 2, t0) is None
     assert solver.linear_field_of(lambda t, z: z, z0, 2, t0) is None
+
+
+def test_scalar_host_locator_equals_the_tensor_one():
+    """solver._host_locator (numpy scalars + bisect, once per field evaluation of the adaptive / adjoint drivers)
+    gives the bits of schedule.locate (torch casts + bucketize) -- also on the knots and one ulp after them."""
+    import numpy as np
+    from torchcde_b200 import solver
+    from torchcde_b200.schedule import locate
+
+    class FakeControl:
+        pass
+
+    gen = torch.Generator().manual_seed(3)
+    for knot_dtype in (torch.float32, torch.float64):
+        for state_dtype in (torch.float32, torch.float64):
+            knots = (torch.rand(40, generator=gen, dtype=torch.float64) + 0.01).cumsum(0).to(knot_dtype)
+            X = FakeControl()
+            orig = (solver._schedule_knots, solver._control_signature)
+            solver._schedule_knots = lambda _x: knots
+            solver._control_signature = lambda _x: ("cubic", (), 1, 39)
+            try:
+                where = solver._host_locator(X, state_dtype)
+            finally:
+                solver._schedule_knots, solver._control_signature = orig
+            times = (torch.rand(500, generator=gen, dtype=torch.float64) * 30 - 2).tolist() + knots.tolist()
+            times += [float(np.nextafter(np.float32(v), np.float32(1e9))) for v in knots.tolist()]
+            for nudge in (0, 1):
+                for t in times:
+                    tt = torch.tensor(t, dtype=torch.float64).to(state_dtype)
+                    if nudge:
+                        tt = torch.nextafter(tt, tt + 1)
+                    frac, index = locate(knots, tt.to(knot_dtype), 39)
+                    assert where(t, nudge) == (int(index), float(frac))

@@ -18,8 +18,11 @@ norm is the RMS over the *whole* state tensor, so a batch shares one step sequen
 linear vector field it is one fused kernel launch (``tcde_vector_field_linear``).
 """
 import bisect
+import ctypes
 
 import torch
+
+from . import _lib
 
 # Dormand-Prince 5(4), FSAL.  alpha, beta (rows), solution weights, error weights, midpoint weights
 _ALPHA = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
@@ -46,13 +49,60 @@ def _rms(x):
     return float(x.pow(2).mean().sqrt())
 
 
+def _kernels_apply(*tensors):
+    """The single-launch kernels serve plain CUDA float tensors of one shape outside autograd; anything else
+    (CPU tensors, states that are being differentiated with adjoint=False) keeps the torch operators."""
+    first = tensors[0]
+    if not (first.is_cuda and first.dtype in (torch.float32, torch.float64) and first.numel() > 0):
+        return False
+    grad = torch.is_grad_enabled()
+    for x in tensors:
+        if x.shape != first.shape or x.dtype != first.dtype or x.device != first.device or not x.is_contiguous():
+            return False
+        if grad and x.requires_grad:
+            return False
+    return True
+
+
+def _term_arrays(ks, coefs):
+    n = len(ks)
+    return (ctypes.c_void_p * n)(*[k.data_ptr() for k in ks]), (ctypes.c_double * n)(*coefs), n
+
+
 def _combine(base, ks, weights, dt):
-    """base + sum_j (weights[j] * dt) * ks[j], skipping zero weights."""
-    out = base
-    for k, w in zip(ks, weights):
-        if w != 0.0:
-            out = out + k * (w * dt)
+    """base + sum_j (weights[j] * dt) * ks[j], skipping zero weights -- one launch of ``tcde_linear_combination``
+    where that applies (``base`` may be None for a pure combination)."""
+    pairs = [(k, w * dt) for k, w in zip(ks, weights) if w != 0.0]
+    terms = [k for k, _ in pairs]
+    if terms and len(terms) <= 7 and _kernels_apply(*(terms + ([base] if base is not None else []))):
+        out = torch.empty_like(terms[0])
+        ptrs, coefs, n = _term_arrays(terms, [c for _, c in pairs])
+        with torch.cuda.device(out.device):
+            _lib.call("tcde_linear_combination", _lib.ptr(out), _lib.ptr(base), ptrs, coefs, n, out.numel(),
+                      _lib.dtype_code(out.dtype), _lib.stream_of(out))
+        return out
+    out = base if base is not None else torch.zeros_like(ks[0])
+    for k, c in pairs:
+        out = out + k * c
     return out
+
+
+def _error_ratio(y0, y1, ks, weights, dt, atol, rtol, norm):
+    """norm(err / (atol + rtol max(|y0|, |y1|))) with err = dt sum_j weights[j] ks[j]; for the default RMS norm one
+    launch of ``tcde_error_ratio_sumsq`` plus the sum of its per-CTA partials (the one host read per attempt)."""
+    pairs = [(k, w * dt) for k, w in zip(ks, weights) if w != 0.0]
+    terms = [k for k, _ in pairs]
+    if norm is _rms and terms and len(terms) <= 7 and _kernels_apply(y0, y1, *terms):
+        n_part = _lib.load().tcde_error_ratio_partials(y0.numel())
+        partials = torch.empty(n_part, dtype=torch.float64, device=y0.device)
+        ptrs, coefs, n = _term_arrays(terms, [c for _, c in pairs])
+        with torch.cuda.device(y0.device):
+            _lib.call("tcde_error_ratio_sumsq", _lib.ptr(y0), _lib.ptr(y1), ptrs, coefs, n, float(atol), float(rtol),
+                      y0.numel(), _lib.dtype_code(y0.dtype), _lib.ptr(partials), _lib.stream_of(y0))
+        return float(partials.sum().div_(y0.numel()).sqrt_())
+    err = _combine(None, ks, weights, dt)
+    tol = atol + rtol * torch.max(y0.abs(), y1.abs())
+    return norm(err / tol)
 
 
 def _initial_step(field, t0, y0, f0, rtol, atol):
@@ -101,9 +151,7 @@ class Dopri5:
             y1 = _combine(y0, ks, beta, dt)
             ks.append(self.field(ti, y1))
         # the last beta row equals the solution weights (FSAL): y1 is the 5th-order solution
-        err = _combine(torch.zeros_like(y0), ks, _C_ERROR, dt)
-        tol = self.atol + self.rtol * torch.max(y0.abs(), y1.abs())
-        return y1, ks, self.norm(err / tol)
+        return y1, ks, _error_ratio(y0, y1, ks, _C_ERROR, dt, self.atol, self.rtol, self.norm)
 
     def integrate(self, times):
         out = [self.y0]
@@ -126,9 +174,11 @@ class Dopri5:
                     step = jumps[0] - t_hi
                 y1, ks, ratio = self._attempt(t_hi, step, y0, f0)
                 if ratio <= 1:
-                    y_mid = _combine(y0, ks, _C_MID, step)
-                    coeff = self._fit(y0, y1, y_mid, ks[0], ks[-1], step)
-                    t_lo, t_hi = t_hi, (jumps[0] if on_jump else t_hi + step)
+                    t_new = jumps[0] if on_jump else t_hi + step
+                    if t_new >= target:          # the dense output is only ever evaluated inside the last step
+                        y_mid = _combine(y0, ks, _C_MID, step)
+                        coeff = self._fit(y0, y1, y_mid, ks[0], ks[-1], step)
+                    t_lo, t_hi = t_hi, t_new
                     y0, f0 = y1, ks[-1]
                     if on_jump:
                         jumps.pop(0)

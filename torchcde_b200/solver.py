@@ -9,8 +9,11 @@ kernel (``tcde_cdeint_fixed_linear``) when the vector field is the README-form l
 any other ``func`` runs through this package's own on-GPU stage loop, which keeps the
 reference's arithmetic but issues no per-stage host syncs.
 """
+import bisect
 import warnings
 import weakref
+
+import numpy as np
 
 import torch
 
@@ -259,13 +262,21 @@ def _host_locator(X, state_dtype):
     ``_interpret_t``), evaluated on the CPU so that no device sync is needed per stage."""
     knots = _schedule_knots(X)
     n_rows = _control_signature(X)[3]
+    # scalar version of ``schedule.locate``: numpy scalars round exactly like the tensor casts, ``bisect_left`` is
+    # ``torch.bucketize`` (right=False), and none of it goes through the torch dispatcher (this runs once per
+    # vector-field evaluation of the adaptive and adjoint drivers)
+    state_t = np.dtype(str(state_dtype).replace("torch.", "")).type
+    knot_t = np.dtype(str(knots.dtype).replace("torch.", "")).type
+    knot_list = knots.tolist()
+    knot_vals = [knot_t(v) for v in knot_list]
 
     def where(t, nudge=0):
-        tt = torch.tensor(t, dtype=torch.float64).to(state_dtype)
+        tt = state_t(t)
         if nudge:
-            tt = torch.nextafter(tt, tt + 1)
-        frac, index = locate(knots, tt.to(knots.dtype), n_rows)
-        return int(index), frac
+            tt = np.nextafter(tt, tt + state_t(1))
+        tk = knot_t(tt)
+        index = min(max(bisect.bisect_left(knot_list, float(tk)) - 1, 0), n_rows - 1)
+        return index, float(tk - knot_vals[index])
 
     return where
 
@@ -369,7 +380,7 @@ def _torch_field(X, func, is_prod, known_control, z0):
         ts = ts.to(y.device)
         if known_control:
             index, frac = where(t, nudge)
-            dx = _derivative_at(X, index, frac.to(y.device))
+            dx = _derivative_at(X, index, frac)
         else:
             dx = X.derivative(ts)
         if is_prod:
