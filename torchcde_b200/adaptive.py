@@ -69,22 +69,25 @@ def _term_arrays(ks, coefs):
     return (ctypes.c_void_p * n)(*[k.data_ptr() for k in ks]), (ctypes.c_double * n)(*coefs), n
 
 
-def _combine(base, ks, weights, dt):
+def _combine(base, ks, weights, dt, out=None):
     """base + sum_j (weights[j] * dt) * ks[j], skipping zero weights -- one launch of ``tcde_linear_combination``
-    where that applies (``base`` may be None for a pure combination)."""
+    where that applies (``base`` may be None for a pure combination; ``out`` may alias ``base``)."""
     pairs = [(k, w * dt) for k, w in zip(ks, weights) if w != 0.0]
     terms = [k for k, _ in pairs]
     if terms and len(terms) <= 7 and _kernels_apply(*(terms + ([base] if base is not None else []))):
-        out = torch.empty_like(terms[0])
+        out = torch.empty_like(terms[0]) if out is None else out
         ptrs, coefs, n = _term_arrays(terms, [c for _, c in pairs])
         with torch.cuda.device(out.device):
             _lib.call("tcde_linear_combination", _lib.ptr(out), _lib.ptr(base), ptrs, coefs, n, out.numel(),
                       _lib.dtype_code(out.dtype), _lib.stream_of(out))
         return out
-    out = base if base is not None else torch.zeros_like(ks[0])
+    res = base if base is not None else torch.zeros_like(ks[0])
     for k, c in pairs:
-        out = out + k * c
-    return out
+        res = res + k * c
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def _error_ratio(y0, y1, ks, weights, dt, atol, rtol, norm):
@@ -334,7 +337,6 @@ def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
     shape = ys[0].shape
     U = torch.empty((2,) + tuple(shape), dtype=ys.dtype, device=ys.device)
     V = torch.empty_like(U)
-    tmp = torch.empty_like(U)
     K = [torch.empty_like(U) for _ in range(4)]
     a_y = grad_ys[-1].clone()
 
@@ -369,20 +371,15 @@ def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
         for lo, hi in zip(grid[:-1], grid[1:]):
             ds = hi - lo
             if method == "rk4":
+                # the 3/8 rule of odeint_fixed, each stage state / the step itself as one combination launch
                 field(index[e], frac[e], U, K[0], ds * 0.125)
-                torch.add(U, K[0], alpha=ds / 3, out=V)
+                _combine(U, K[:1], (1.0 / 3,), ds, out=V)
                 field(index[e + 1], frac[e + 1], V, K[1], ds * 0.375)
-                torch.add(K[1], K[0], alpha=-1.0 / 3, out=tmp)
-                torch.add(U, tmp, alpha=ds, out=V)
+                _combine(U, K[:2], (-1.0 / 3, 1.0), ds, out=V)
                 field(index[e + 2], frac[e + 2], V, K[2], ds * 0.375)
-                torch.sub(K[0], K[1], out=tmp)
-                tmp.add_(K[2])
-                torch.add(U, tmp, alpha=ds, out=V)
+                _combine(U, K[:3], (1.0, -1.0, 1.0), ds, out=V)
                 field(index[e + 3], frac[e + 3], V, K[3], ds * 0.125)
-                torch.add(K[1], K[2], out=tmp)
-                torch.add(K[0], tmp, alpha=3.0, out=tmp)
-                tmp.add_(K[3])
-                U.add_(tmp, alpha=ds * 0.125)
+                _combine(U, K, (0.125, 0.375, 0.375, 0.125), ds, out=U)
                 e += 4
             elif method == "midpoint":
                 field(index[e], frac[e], U, K[0], 0.0)

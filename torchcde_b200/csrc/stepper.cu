@@ -22,7 +22,7 @@ template <typename T> struct Terms {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-combine_kernel(T* __restrict__ out, const T* __restrict__ base, const Terms<T> terms, int64_t n) {
+combine_kernel(T* out, const T* base, const Terms<T> terms, int64_t n) {     // out may alias base
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += stride) {
         T v = base ? base[i] : T(0);
