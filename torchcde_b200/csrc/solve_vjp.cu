@@ -198,18 +198,28 @@ field_vjp_kernel(const float* __restrict__ control, int control_kind, int64_t n_
     }
 }
 
-// grad[e] += scale * sum over CTAs of scratch[cta][e]
+// grad[e] += scale * sum over CTAs of scratch[cta][e].  A CTA owns 32 elements; each of its 8 warps sums every
+// 8th CTA's partial (128-byte coalesced rows), then warp 0 adds the 8 results in a fixed order: 8,448 elements x
+// ~300 partial sums are a latency problem, not a bandwidth one, and one thread per element left most SMs idle.
 __global__ void __launch_bounds__(256)
 field_vjp_reduce_kernel(const float* __restrict__ scratch, int n_ctas, float scale, float* __restrict__ grad_weight,
                         float* __restrict__ grad_bias) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= kParams) return;
+    __shared__ float parts[8][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int cta = 0; cta < n_ctas; ++cta) s += scratch[(size_t)cta * kParams + e];
+    if (e < kParams)
+        for (int cta = part; cta < n_ctas; cta += 8) s += scratch[(size_t)cta * kParams + e];
+    parts[part][lane] = s;
+    __syncthreads();
+    if (part != 0 || e >= kParams) return;
+    float total = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) total += parts[w][lane];
     if (e < H * C * H) {
-        if (grad_weight) grad_weight[e] += scale * s;
+        if (grad_weight) grad_weight[e] += scale * total;
     } else if (grad_bias) {
-        grad_bias[e - H * C * H] += scale * s;
+        grad_bias[e - H * C * H] += scale * total;
     }
 }
 
@@ -258,7 +268,7 @@ extern "C" int tcde_vector_field_linear_vjp(const void* control, int control_kin
         (float)f_scale, (float)vjp_scale);
     TCDE_CHECK_CUDA(cudaGetLastError());
     if (grad_weight || grad_bias) {
-        vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 255) / 256, 256, 0, s>>>((const float*)scratch, grid, (float)grad_scale,
+        vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 31) / 32, 256, 0, s>>>((const float*)scratch, grid, (float)grad_scale,
                                                                                 (float*)grad_weight, (float*)grad_bias);
         TCDE_CHECK_CUDA(cudaGetLastError());
     }
