@@ -4,7 +4,6 @@ import math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torchcde_b200 as cde
-from torchcde_b200 import adaptive
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 L, C, H = 256, 8, 32

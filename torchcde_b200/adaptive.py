@@ -17,7 +17,6 @@ norm is the RMS over the *whole* state tensor, so a batch shares one step sequen
 (SURVEY.md 8e caveat 1).  The vector field is a callable ``field(t_float, y) -> dy``; for the
 linear vector field it is one fused kernel launch (``tcde_vector_field_linear``).
 """
-import bisect
 import ctypes
 
 import torch
