@@ -67,17 +67,24 @@ def cdeint_from_host(control_host, func, z0_host, t, out_host=None, kind="cubic"
 
 class SeriesPipeline:
     """Persistent streams and staging buffers for ``cdeint_from_host_series`` (reused across calls:
-    creating streams / device buffers per call would go through cudaMalloc every time)."""
+    creating streams / device buffers per call would go through cudaMalloc every time).
+
+    Four slots, not two: a chunk's solve (one CTA-time, ~2.3 ms at the BASELINE shapes, whatever the chunk size)
+    takes longer than its copy (1.2 ms for 8,192 series), and a slot's next copy has to wait for that slot's
+    previous solve -- with two slots the PCIe link idles half the time, with four the copies run back to back."""
+
+    SLOTS = 4
 
     def __init__(self, device, chunk_paths, length, channels, hidden, dtype):
         self.device = torch.device(device)
         self.chunk_paths = chunk_paths
         self.key = (chunk_paths, length, channels, hidden, dtype)
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
-        self.x = [torch.empty(chunk_paths, length, channels, dtype=dtype, device=self.device) for _ in range(2)]
-        self.z0 = [torch.empty(chunk_paths, hidden, dtype=dtype, device=self.device) for _ in range(2)]
+        n = self.SLOTS
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n)]
+        self.x = [torch.empty(chunk_paths, length, channels, dtype=dtype, device=self.device) for _ in range(n)]
+        self.z0 = [torch.empty(chunk_paths, hidden, dtype=dtype, device=self.device) for _ in range(n)]
         self.coeffs = [torch.empty(chunk_paths, length - 1, 4 * channels, dtype=dtype, device=self.device)
-                       for _ in range(2)]
+                       for _ in range(n)]
 
 
 _series_pipelines = {}
@@ -114,7 +121,7 @@ def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths
     with torch.no_grad():
         for i, lo in enumerate(range(0, n_paths, cp)):
             hi = min(lo + cp, n_paths)
-            slot = i & 1
+            slot = i % pipe.SLOTS
             with torch.cuda.stream(pipe.streams[slot]):
                 n = hi - lo
                 x_dev, z_dev, coeffs = pipe.x[slot][:n], pipe.z0[slot][:n], pipe.coeffs[slot][:n]
