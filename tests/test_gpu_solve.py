@@ -361,3 +361,35 @@ def test_control_with_own_knots_on_device():
                                func.linear.bias.detach().cpu().double(), z0.float().double(),
                                torch.stack([knots.float()[0], knots.float()[-1]]).double(), "rk4", 0.25)
     _assert_close(out, want, torch.float32)
+
+
+@pytest.mark.parametrize("batch,chunk", [(700, 256), (1000, 96), (64, 4096)])
+def test_host_pipelines_equal_the_device_resident_solve(batch, chunk):
+    """hostio.cdeint_from_host / cdeint_from_host_series (chunked H2D -> [coefficients ->] solve -> D2H on several
+    streams) return the bits of one device-resident cdeint: paths are independent, chunking changes nothing.
+    Chunk counts above and below the number of pipeline slots, ragged last chunk, buffers reused across calls."""
+    from torchcde_b200 import hostio
+    gen = torch.Generator().manual_seed(batch)
+    length, channels, hidden = 24, 8, 32
+    x = (torch.randn(batch, length, channels, generator=gen).cumsum(1) / math.sqrt(length))
+    z0 = torch.randn(batch, hidden, generator=gen)
+    torch.manual_seed(4)
+    func = cde.LinearVectorField(hidden, channels).to(DEV)
+    t = torch.tensor([0.0, 7.5, length - 1.0])
+    kw = dict(method="rk4", options={"step_size": 0.5})
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x.to(DEV))
+        want = cde.cdeint(cde.CubicSpline(coeffs), func, z0.to(DEV), t, adjoint=False, **kw).cpu()
+        x_host, z_host, c_host = x.pin_memory(), z0.pin_memory(), coeffs.cpu().pin_memory()
+        for _ in range(2):                                       # second round: cached pipeline buffers
+            got = hostio.cdeint_from_host(c_host, func, z_host, t, chunk_paths=chunk, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want)
+            got = hostio.cdeint_from_host_series(x_host, func, z_host, t, chunk_paths=chunk, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want)
+        lin = cde.LinearInterpolation(x.to(DEV))
+        want_lin = cde.cdeint(lin, func, z0.to(DEV), t, adjoint=False, **kw).cpu()
+        got = hostio.cdeint_from_host(x_host, func, z_host, t, kind="linear", chunk_paths=chunk, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want_lin)
