@@ -171,6 +171,31 @@ TCDE_API int tcde_cdeint_fixed_linear(const void* control, int control_kind, int
                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
                              double sign, int dtype, void* stream);
 
+/* tcde_cdeint_fixed_linear that also stores the INPUT of every stage:
+ * stage_dump[n_steps * n_stages][n_paths][hidden].  Served by the tensor-core kernel only (fp32, hidden = 32,
+ * channels = 8, 16-byte aligned buffers; TCDE_ERR_UNSUPPORTED otherwise).  The backward solve of odeint_adjoint
+ * uses it twice: for a linear field the adjoint state a obeys da/ds = a^T df/dz, which does not involve z, so
+ * z(s) and a(s) are two ordinary solves (the second with the regrouped, negated weight and no bias). */
+TCDE_API int tcde_cdeint_fixed_linear_stages(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                                    const void* bias, const void* z0, void* out, void* stage_dump, int64_t n_paths,
+                                    int64_t channels, int64_t hidden, int method, int64_t n_steps, const void* step_dt,
+                                    const int32_t* stage_index, const void* stage_frac, int64_t n_out,
+                                    const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
+                                    double sign, int dtype, void* stream);
+
+/* ... and the parameter gradients of that whole backward solve in one launch:
+ *   grad_weight[h*C+c][k] += scale * sum_e sum_p stage_weight[e] * a_stages[e][p][h] * dXdt_e[p][c] * z_stages[e][p][k]
+ *   grad_bias[h*C+c]      += scale * sum_e sum_p stage_weight[e] * a_stages[e][p][h] * dXdt_e[p][c]
+ * with dXdt_e from the control at (stage_index[e], stage_frac[e]) and stage_weight[e] = step * Runge-Kutta weight
+ * (device arrays of length n_stages_total).  fp32, hidden = 32, channels = 8. */
+TCDE_API int64_t tcde_linear_field_param_grads_scratch_bytes(int64_t n_paths, int64_t n_stages_total, int64_t channels,
+                                                    int64_t hidden);
+TCDE_API int tcde_linear_field_param_grads(const void* control, int control_kind, int64_t n_rows, const void* z_stages,
+                                  const void* a_stages, const int32_t* stage_index, const void* stage_frac,
+                                  const void* stage_weight, int64_t n_stages_total, void* grad_weight, void* grad_bias,
+                                  void* scratch, int64_t n_paths, int64_t channels, int64_t hidden, double scale,
+                                  int dtype, void* stream);
+
 /* Elementwise pieces of the adaptive driver that stands in for torchdiffeq's dopri5 (the reference's default
  * method, solver.py:226-227): out[i] = base[i] + sum_j coefs[j] * terms[j][i]  (base may be NULL; at most 7
  * terms; `terms` / `coefs` are HOST arrays of device pointers / doubles, read at launch). */

@@ -316,3 +316,44 @@ def test_stepper_kernels_against_torch(dtype, shape):
     yg = y0.clone().requires_grad_(True)
     out = adaptive._combine(yg, ks, weights, dt)
     assert out.requires_grad
+
+
+@pytest.mark.parametrize("method", ["rk4", "midpoint", "euler"])
+def test_trajectory_backward_matches_the_per_stage_backward(method, monkeypatch):
+    """Fixed-step adjoint at the flagship field shape: the three-launch backward (two tensor-core solves that keep
+    their stage inputs + one contraction into dL/dW, dL/db) vs the per-stage fused backward vs autograd."""
+    from torchcde_b200 import solver
+    x, z0, func = _problem(300, 14, 8, 32, seed=11)
+    func = func.to(DEV)
+    with torch.no_grad():
+        X = cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x.to(DEV)))
+    t = torch.tensor([0.0, 4.5, 13.0])
+    kw = {"options": {"step_size": 0.5}}
+    real = solver._kernel_vjp
+    grads, used = {}, {}
+    for mode in ("trajectory", "per_stage", "autograd"):
+        def probe(*args, _mode=mode, **kwargs):
+            stage = real(*args, **kwargs)
+            if _mode == "autograd":
+                return None
+            if _mode == "per_stage":
+                stage.segment = lambda *a, **k: None
+            else:
+                inner = stage.segment
+
+                def counted(*a, **k):
+                    res = inner(*a, **k)
+                    used[_mode] = used.get(_mode, 0) + (res is not None)
+                    return res
+                stage.segment = counted
+            return stage
+        monkeypatch.setattr(solver, "_kernel_vjp", probe)
+        zz = z0.to(DEV).clone().requires_grad_(True)
+        func.zero_grad()
+        out = cde.cdeint(X, func, zz, t, adjoint=True, method=method, **kw)
+        (out[:, 1].pow(2).sum() + out[:, 2].sum()).backward()
+        grads[mode] = (zz.grad.clone(), func.linear.weight.grad.clone(), func.linear.bias.grad.clone())
+    assert used.get("trajectory") == 2                        # both segments took the three-launch route
+    for mode in ("per_stage", "autograd"):
+        for got, want in zip(grads["trajectory"], grads[mode]):
+            assert torch.allclose(got, want, rtol=2e-3, atol=2e-4 * float(want.abs().max())), mode

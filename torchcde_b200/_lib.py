@@ -38,6 +38,11 @@ SIGNATURES = {
     "tcde_vector_field_linear_vjp_scratch_bytes": ([_i64, _i64, _i64], _i64),
     "tcde_vector_field_linear_vjp": ([_p, _int, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _dbl,
                                       _dbl, _dbl, _dbl, _int, _p], _int),
+    "tcde_cdeint_fixed_linear_stages": ([_p, _int, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, _int, _i64, _p, _p, _p,
+                                         _i64, _p, _p, _p, _dbl, _int, _p], _int),
+    "tcde_linear_field_param_grads_scratch_bytes": ([_i64, _i64, _i64, _i64], _i64),
+    "tcde_linear_field_param_grads": ([_p, _int, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _dbl,
+                                       _int, _p], _int),
     "tcde_linear_combination": ([_p, _p, _p, _p, _int, _i64, _int, _p], _int),
     "tcde_error_ratio_partials": ([_i64], _i64),
     "tcde_error_ratio_sumsq": ([_p, _p, _p, _p, _int, _dbl, _dbl, _i64, _int, _p, _p], _int),

@@ -347,6 +347,11 @@ def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
             stage.launch(idx, frac, state[0], state[1], out[0], out[1], gw, gb, -1.0, 1.0, weight)
 
     for i in range(len(times) - 1, 0, -1):
+        # whole segment in three launches (two tensor-core solves that keep their stage inputs + one contraction)
+        a_lo = stage.segment(times[i], times[i - 1], ys[i], a_y, method, step_size, gw, gb)
+        if a_lo is not None:
+            a_y = a_lo + grad_ys[i - 1]
+            continue
         s0, s_end = -times[i], -times[i - 1]
         if step_size is None:
             grid = [s0, s_end]

@@ -90,4 +90,27 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- arguments of the tensor-core solve (solve_umma.cu), filled in by the C entry points of solve_simt.cu ----
+struct UmmaArgs {
+    const float* control;
+    const float* weight;
+    const float* bias;
+    const float* z0;
+    float* out;
+    const float* step_dt;
+    const int32_t* stage_index;
+    const float* stage_frac;
+    const int32_t* out_step;
+    const int32_t* out_mode;
+    const float* out_slope;
+    int64_t n_paths;
+    int64_t n_rows;
+    int control_kind, method, n_stages, n_steps, n_out;
+    float sign;
+    long long* trace;     // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
+    float* stage_dump;    // optional [n_steps * n_stages][n_paths][32]: the input of every stage (for the adjoint)
+};
+bool solve_umma_supported(int H, int C);
+int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
+
 }  // namespace tcde

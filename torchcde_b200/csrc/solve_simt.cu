@@ -501,18 +501,6 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
 }
 
 // ---- tensor-core variant (solve_umma.cu) -------------------------------------------------------
-struct UmmaArgs {
-    const float* control; const float* weight; const float* bias; const float* z0; float* out;
-    const float* step_dt; const int32_t* stage_index; const float* stage_frac;
-    const int32_t* out_step; const int32_t* out_mode; const float* out_slope;
-    int64_t n_paths; int64_t n_rows;
-    int control_kind, method, n_stages, n_steps, n_out;
-    float sign;
-    long long* trace;
-};
-bool solve_umma_supported(int H, int C);
-int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
-
 static long long* g_trace = nullptr;   // profiling aid: device buffer for in-kernel clock stamps (see tcde_set_trace_buffer)
 static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
 
@@ -549,12 +537,12 @@ extern "C" int tcde_vector_field_linear(const void* control, int control_kind, i
                                 (int)hidden, index, frac, s);
 }
 
-extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
-                                        const void* bias, const void* z0, void* out, int64_t n_paths, int64_t channels,
-                                        int64_t hidden, int method, int64_t n_steps, const void* step_dt,
-                                        const int32_t* stage_index, const void* stage_frac, int64_t n_out,
-                                        const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
-                                        double sign, int dtype, void* stream) {
+static int solve_fixed_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                              const void* bias, const void* z0, void* out, int64_t n_paths, int64_t channels,
+                              int64_t hidden, int method, int64_t n_steps, const void* step_dt,
+                              const int32_t* stage_index, const void* stage_frac, int64_t n_out,
+                              const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
+                              double sign, int dtype, void* stage_dump, void* stream) {
     TCDE_CHECK_ARG(control && weight && bias && z0 && out, "null data pointer");
     TCDE_CHECK_ARG(step_dt && stage_index && stage_frac && out_step && out_mode && out_slope, "null schedule pointer");
     TCDE_CHECK_ARG(n_paths >= 0 && channels >= 1 && hidden >= 1 && n_rows >= 1, "bad sizes");
@@ -578,18 +566,45 @@ extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, i
             UmmaArgs u{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0, (float*)out,
                        (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
-                       (int)n_out, (float)sign, g_trace};
+                       (int)n_out, (float)sign, g_trace, (float*)stage_dump};
             return solve_umma_f32(u, (int)hidden, (int)channels, s);
         }
+        TCDE_CHECK_SUPPORTED(stage_dump == nullptr, "the stage dump is written by the tensor-core solve only "
+                             "(fp32, hidden=32, channels=8, 16-byte aligned buffers)");
         SolveArgs<float> a{(const float*)control, (const float*)weight, (const float*)bias, (const float*)z0,
                            (float*)out, (const float*)step_dt, stage_index, (const float*)stage_frac, out_step,
                            out_mode, (const float*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
                            control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (float)sign, 0, 0, 0.f};
         return solve_simt_f32(a, s);
     }
+    TCDE_CHECK_SUPPORTED(stage_dump == nullptr, "the stage dump is written by the fp32 tensor-core solve only");
     SolveArgs<double> a{(const double*)control, (const double*)weight, (const double*)bias, (const double*)z0,
                         (double*)out, (const double*)step_dt, stage_index, (const double*)stage_frac, out_step,
                         out_mode, (const double*)out_slope, n_paths, n_rows, (int)channels, 0, (int)hidden,
                         control_kind, method, n_stages, (int)n_steps, (int)n_out, 0, 0, (double)sign, 0, 0, 0.0};
     return solve_simt_f64(a, s);
+}
+
+extern "C" int tcde_cdeint_fixed_linear(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                                        const void* bias, const void* z0, void* out, int64_t n_paths, int64_t channels,
+                                        int64_t hidden, int method, int64_t n_steps, const void* step_dt,
+                                        const int32_t* stage_index, const void* stage_frac, int64_t n_out,
+                                        const int32_t* out_step, const int32_t* out_mode, const void* out_slope,
+                                        double sign, int dtype, void* stream) {
+    return solve_fixed_linear(control, control_kind, n_rows, weight, bias, z0, out, n_paths, channels, hidden, method,
+                              n_steps, step_dt, stage_index, stage_frac, n_out, out_step, out_mode, out_slope, sign, dtype,
+                              nullptr, stream);
+}
+
+extern "C" int tcde_cdeint_fixed_linear_stages(const void* control, int control_kind, int64_t n_rows, const void* weight,
+                                               const void* bias, const void* z0, void* out, void* stage_dump,
+                                               int64_t n_paths, int64_t channels, int64_t hidden, int method,
+                                               int64_t n_steps, const void* step_dt, const int32_t* stage_index,
+                                               const void* stage_frac, int64_t n_out, const int32_t* out_step,
+                                               const int32_t* out_mode, const void* out_slope, double sign, int dtype,
+                                               void* stream) {
+    TCDE_CHECK_ARG(stage_dump != nullptr, "null stage dump");
+    return solve_fixed_linear(control, control_kind, n_rows, weight, bias, z0, out, n_paths, channels, hidden, method,
+                              n_steps, step_dt, stage_index, stage_frac, n_out, out_step, out_mode, out_slope, sign, dtype,
+                              stage_dump, stream);
 }

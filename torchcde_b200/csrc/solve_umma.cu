@@ -30,25 +30,6 @@
 
 namespace tcde {
 
-struct UmmaArgs {
-    const float* control;
-    const float* weight;
-    const float* bias;
-    const float* z0;
-    float* out;
-    const float* step_dt;
-    const int32_t* stage_index;
-    const float* stage_frac;
-    const int32_t* out_step;
-    const int32_t* out_mode;
-    const float* out_slope;
-    int64_t n_paths;
-    int64_t n_rows;
-    int control_kind, method, n_stages, n_steps, n_out;
-    float sign;
-    long long* trace;    // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
-};
-
 namespace umma {
 
 constexpr int kH = 32;            // hidden channels == K of the MMA == one 128-byte swizzled row
@@ -165,7 +146,7 @@ template <int N> struct Smem {
     static constexpr int total = bars + 64;
 };
 
-template <int C, bool TRACE>
+template <int C, bool TRACE, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs a) {
     constexpr int N = kH * C;
     static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
@@ -285,7 +266,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
                 cp_async_commit();
             };
-            auto write_a = [&](const float* z) {          // next stage input -> swizzled hi / lo rows
+            auto write_a = [&](const float* z, int stage_no) {   // next stage input -> swizzled hi / lo rows
+                if (DUMP && live) {                       // ... and, for the adjoint, to the trajectory in HBM
+                    float4* dst = reinterpret_cast<float4*>(a.stage_dump + ((int64_t)stage_no * a.n_paths + path) * kH);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
+                }
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float4 hi, lo;
@@ -325,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                 next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
             }
             fetch_row(a.stage_index[0]);
-            write_a(y);
+            write_a(y, 0);
 
             const float third = (float)(1.0 / 3.0);
             int step = 0, sub = 0;
@@ -462,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_umma_kernel(const UmmaArgs
                     step_done = true;
                 }
                 if (tr) a.trace[st * 8 + 5] = clock64();
-                if (more) write_a(zn);                    // hand the next stage to the tensor core first ...
+                if (more) write_a(zn, st + 1);            // hand the next stage to the tensor core first ...
                 if (tr) a.trace[st * 8 + 6] = clock64();
                 if (step_done) {                          // ... then the bookkeeping that nobody waits for
                     while (next_out == step) {
@@ -509,7 +495,10 @@ int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream) {
     const int64_t per_cta = umma::kTile * umma::kTiles;
     const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
     TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
-    auto kern = a.trace ? umma::cdeint_umma_kernel<8, true> : umma::cdeint_umma_kernel<8, false>;
+    auto kern = a.stage_dump ? umma::cdeint_umma_kernel<8, false, true>
+                             : a.trace ? umma::cdeint_umma_kernel<8, true, false> : umma::cdeint_umma_kernel<8, false, false>;
+    TCDE_CHECK_SUPPORTED(a.stage_dump == nullptr || (reinterpret_cast<uintptr_t>(a.stage_dump) & 15) == 0,
+                         "tensor-core solve: the stage dump must be 16-byte aligned");
     constexpr int smem = umma::Smem<256>::total + 1024;     // slack for the 1024-byte alignment of the tiles
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(unsigned)ctas, umma::kThreads, smem, stream>>>(a);

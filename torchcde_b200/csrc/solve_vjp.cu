@@ -223,6 +223,102 @@ field_vjp_reduce_kernel(const float* __restrict__ scratch, int n_ctas, float sca
     }
 }
 
+// The parameter gradients of a WHOLE fixed-step backward solve in one launch, from the stage inputs that the
+// two decoupled tensor-core solves left in HBM.  For the linear field the adjoint state does not depend on z
+// (da/ds = a^T df/dz has no z in it), so z and a are each an ordinary fused solve; what couples them is only
+//     dL/dW[hC+c][k] = sum over stages e, paths p of  w_e a_e[p][h] dX_e[p][c] z_e[p][k]       (w_e = ds * RK weight)
+// Work item = (stage, tile of 64 paths); a persistent CTA keeps its 8 x 4 block per thread in registers over all
+// its items, exactly like the per-stage kernel above, and leaves per-CTA partial sums in scratch.
+__global__ void __launch_bounds__(kThreads, 3)
+param_grad_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ z_stages,
+                  const float* __restrict__ a_stages, const int32_t* __restrict__ stage_index,
+                  const float* __restrict__ stage_frac, const float* __restrict__ stage_weight, int n_stage_total,
+                  float* __restrict__ scratch, int64_t n_paths) {
+    __shared__ __align__(16) float zR[TB * H];
+    __shared__ __align__(16) float aR[TB * H];
+    __shared__ __align__(16) float dxs[TB * C];
+    using E = exact<float>;
+    const int tid = threadIdx.x;
+    const bool cubic = (control_kind == TCDE_CONTROL_CUBIC);
+    const int row_stride = cubic ? 4 * C : C;
+    const int gh = tid & 31, gkt = tid >> 5;
+    float gw[C][4], gb[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        gb[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gw[c][j] = 0.f;
+    }
+    const int64_t n_tiles = (n_paths + TB - 1) / TB;
+    const int64_t n_items = n_tiles * n_stage_total;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int e = (int)(item / n_tiles);
+        const int64_t path0 = (item - (int64_t)e * n_tiles) * TB;
+        const float we = stage_weight[e];
+        if (we == 0.f) continue;                  // e.g. the first stage of the midpoint rule (uniform per CTA)
+        const int index = stage_index[e];
+        const float frac = stage_frac[e];
+        __syncthreads();                          // the previous item is done with the tiles
+        const float* zs = z_stages + ((int64_t)e * n_paths + path0) * H;
+        const float* as = a_stages + ((int64_t)e * n_paths + path0) * H;
+        for (int v = tid; v < TB * (H / 4); v += kThreads) {
+            const int lp = v >> 3;
+            F4 zv = {{0.f, 0.f, 0.f, 0.f}}, av = zv;
+            if (path0 + lp < n_paths) {
+                zv = *reinterpret_cast<const F4*>(zs + 4 * v);
+                av = *reinterpret_cast<const F4*>(as + 4 * v);
+            }
+            *reinterpret_cast<F4*>(zR + 4 * v) = zv;
+            *reinterpret_cast<F4*>(aR + 4 * v) = av;
+        }
+        for (int v = tid; v < TB * Q; v += kThreads) {
+            const int lp = v / Q, q = v - lp * Q;
+            int64_t p = path0 + lp;
+            if (p >= n_paths) p = n_paths - 1;
+            const float* r = control + (p * n_rows + index) * row_stride + (cubic ? C : 0) + 4 * q;
+            F4 o;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {         // dX/dt (interpolation_cubic.py:331-336), times the stage's weight
+                const float d = cubic ? E::add(r[j], E::mul(E::add(r[C + j], E::mul(r[2 * C + j], frac)), frac)) : r[j];
+                o.v[j] = d * we;
+            }
+            *reinterpret_cast<F4*>(dxs + lp * C + 4 * q) = o;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int lp = 0; lp < TB; ++lp) {
+            const float av = aR[lp * H + gh];
+            const F4 d0 = *reinterpret_cast<const F4*>(dxs + lp * C);
+            const F4 d1 = *reinterpret_cast<const F4*>(dxs + lp * C + 4);
+            const F4 z4 = *reinterpret_cast<const F4*>(zR + lp * H + 4 * gkt);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float ad = av * (c < 4 ? d0.v[c] : d1.v[c - 4]);
+                if (gkt == 0) gb[c] += ad;        // warp-uniform: one warp per row block owns the bias gradient
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gw[c][j] = fmaf(ad, z4.v[j], gw[c][j]);
+            }
+        }
+    }
+    float* mine = scratch + (size_t)blockIdx.x * kParams;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        F4 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.v[j] = gw[c][j];
+        *reinterpret_cast<F4*>(mine + ((size_t)gh * C + c) * H + 4 * gkt) = o;
+        if (gkt == 0) mine[H * C * H + gh * C + c] = gb[c];
+    }
+}
+
+static int param_grad_grid(int64_t n_paths, int64_t n_stage_total) {
+    const int64_t items = ((n_paths + TB - 1) / TB) * n_stage_total;
+    int64_t g = (int64_t)sm_count() * 3;
+    if (g > items) g = items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
 static int vjp_grid(int64_t n_paths) {
     int64_t tiles = (n_paths + TB - 1) / TB;
     int64_t g = (int64_t)sm_count() * 2;
@@ -270,6 +366,43 @@ extern "C" int tcde_vector_field_linear_vjp(const void* control, int control_kin
     if (grad_weight || grad_bias) {
         vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 31) / 32, 256, 0, s>>>((const float*)scratch, grid, (float)grad_scale,
                                                                                 (float*)grad_weight, (float*)grad_bias);
+        TCDE_CHECK_CUDA(cudaGetLastError());
+    }
+    return TCDE_OK;
+}
+
+extern "C" int64_t tcde_linear_field_param_grads_scratch_bytes(int64_t n_paths, int64_t n_stages_total, int64_t channels,
+                                                              int64_t hidden) {
+    if (n_paths < 0 || n_stages_total < 1 || channels != vjp::C || hidden != vjp::H) return -1;
+    return (int64_t)vjp::param_grad_grid(n_paths, n_stages_total) * vjp::kParams * (int64_t)sizeof(float);
+}
+
+extern "C" int tcde_linear_field_param_grads(const void* control, int control_kind, int64_t n_rows, const void* z_stages,
+                                             const void* a_stages, const int32_t* stage_index, const void* stage_frac,
+                                             const void* stage_weight, int64_t n_stages_total, void* grad_weight,
+                                             void* grad_bias, void* scratch, int64_t n_paths, int64_t channels,
+                                             int64_t hidden, double scale, int dtype, void* stream) {
+    TCDE_CHECK_ARG(control && z_stages && a_stages && stage_index && stage_frac && stage_weight && scratch,
+                   "null data pointer");
+    TCDE_CHECK_ARG(n_paths >= 0 && n_rows >= 1 && n_stages_total >= 1 && n_stages_total < (1ll << 31), "bad sizes");
+    TCDE_CHECK_ARG(control_kind == TCDE_CONTROL_CUBIC || control_kind == TCDE_CONTROL_LINEAR, "control_kind=%d",
+                   control_kind);
+    TCDE_CHECK_SUPPORTED(dtype == TCDE_F32 && hidden == vjp::H && channels == vjp::C,
+                         "built for fp32, hidden=%d, channels=%d (got dtype=%d, hidden=%lld, channels=%lld)", vjp::H,
+                         vjp::C, dtype, (long long)hidden, (long long)channels);
+    TCDE_CHECK_ARG(((reinterpret_cast<uintptr_t>(z_stages) | reinterpret_cast<uintptr_t>(a_stages) |
+                     reinterpret_cast<uintptr_t>(scratch)) & 15) == 0, "stage buffers and scratch must be 16-byte aligned");
+    if (n_paths == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = vjp::param_grad_grid(n_paths, n_stages_total);
+    vjp::param_grad_kernel<<<grid, vjp::kThreads, 0, s>>>((const float*)control, control_kind, n_rows,
+                                                         (const float*)z_stages, (const float*)a_stages, stage_index,
+                                                         (const float*)stage_frac, (const float*)stage_weight,
+                                                         (int)n_stages_total, (float*)scratch, n_paths);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    if (grad_weight || grad_bias) {
+        vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 31) / 32, 256, 0, s>>>((const float*)scratch, grid, (float)scale,
+                                                                              (float*)grad_weight, (float*)grad_bias);
         TCDE_CHECK_CUDA(cudaGetLastError());
     }
     return TCDE_OK;

@@ -362,8 +362,60 @@ def _kernel_vjp(X, weight, bias, z0, params):
         frac, index = locate(knots, tt.to(knots.dtype), n_rows)
         return index.tolist(), frac.tolist()
 
+    regrouped = []            # -W with rows regrouped as (k, c) and columns h: the "weight" of the adjoint state's own CDE
+
+    def segment(t_hi, t_lo, y_hi, a_hi, method, step_size, gw, gb):
+        """One segment [t_hi -> t_lo] of a fixed-step backward solve WITHOUT a launch per stage.  For this linear
+        field d a/ds = a^T df/dz does not involve z, so z(s) and a(s) are two ordinary fused solves (tensor-core
+        kernel, reversed time), each leaving the input of every stage in HBM; one more launch contracts the two
+        trajectories with dX/dt and the Runge-Kutta weights into dL/dW, dL/db.  Returns a(t_lo), or None when the
+        tensor-core kernel or the memory for the two trajectories (2 x stages x paths x 128 bytes) is not available."""
+        lib = _lib.load()
+        yf = y_hi.reshape(-1, hidden).contiguous()
+        af = a_hi.reshape(-1, hidden).contiguous()
+        n_paths = yf.size(0)
+        tt = torch.tensor([t_hi, t_lo], dtype=torch.float64)
+        sched, (_floats, _ints, v) = _schedules.get(tt, knots, n_rows, method, step_size, z0.dtype, z0.device)
+        n_total = sched.n_steps * sched.n_stages
+        scratch_bytes = lib.tcde_linear_field_param_grads_scratch_bytes(n_paths, n_total, channels, hidden)
+        if scratch_bytes < 0:
+            return None
+        need = 2 * n_total * n_paths * hidden * 4
+        with torch.cuda.device(z0.device):
+            free, _total = torch.cuda.mem_get_info()
+            if need + scratch_bytes > 0.7 * free:
+                return None
+            if not regrouped:
+                regrouped.append(w.view(hidden, channels, hidden).permute(2, 1, 0).contiguous()
+                                 .view(hidden * channels, hidden).neg_())
+                regrouped.append(torch.zeros_like(b))
+            z_stages = torch.empty(n_total, n_paths, hidden, dtype=z0.dtype, device=z0.device)
+            a_stages = torch.empty_like(z_stages)
+            ends = torch.empty(2, n_paths, sched.n_out, hidden, dtype=z0.dtype, device=z0.device)
+            try:
+                for which, (start, dump, ww, bb) in enumerate(((yf, z_stages, w, b),
+                                                               (af, a_stages, regrouped[0], regrouped[1]))):
+                    _lib.call("tcde_cdeint_fixed_linear_stages", _lib.ptr(control), kind, n_rows, _lib.ptr(ww),
+                              _lib.ptr(bb), _lib.ptr(start), _lib.ptr(ends[which]), _lib.ptr(dump), n_paths, channels,
+                              hidden, _lib.METHODS[method], sched.n_steps, _lib.ptr(v["step_dt"]),
+                              _lib.ptr(v["stage_index"]), _lib.ptr(v["stage_frac"]), sched.n_out,
+                              _lib.ptr(v["out_step"]), _lib.ptr(v["out_mode"]), _lib.ptr(v["out_slope"]),
+                              float(sched.sign), code, _lib.stream_of(yf))
+            except NotImplementedError:
+                return None
+            rk = {"rk4": (0.125, 0.375, 0.375, 0.125), "midpoint": (0.0, 1.0), "euler": (1.0,)}[method]
+            weights = (sched.step_dt.to(torch.float64).unsqueeze(1) * torch.tensor(rk, dtype=torch.float64)).reshape(-1)
+            weights = weights.to(z0.dtype).to(z0.device)
+            scratch2 = torch.empty(max(scratch_bytes // 4, 4), dtype=torch.float32, device=z0.device)
+            _lib.call("tcde_linear_field_param_grads", _lib.ptr(control), kind, n_rows, _lib.ptr(z_stages),
+                      _lib.ptr(a_stages), _lib.ptr(v["stage_index"]), _lib.ptr(v["stage_frac"]), _lib.ptr(weights),
+                      n_total, _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(scratch2), n_paths, channels, hidden, 1.0, code,
+                      _lib.stream_of(yf))
+        return ends[1][:, -1].reshape(a_hi.shape)
+
     stage.launch = launch
     stage.locate_many = locate_many
+    stage.segment = segment
     stage.roles = roles
     stage.new_grads = lambda: [torch.zeros_like(w) if r == "w" else torch.zeros_like(b) for r in roles]
     return stage
