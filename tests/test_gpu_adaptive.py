@@ -357,3 +357,57 @@ def test_trajectory_backward_matches_the_per_stage_backward(method, monkeypatch)
     for mode in ("per_stage", "autograd"):
         for got, want in zip(grads["trajectory"], grads[mode]):
             assert torch.allclose(got, want, rtol=2e-3, atol=2e-4 * float(want.abs().max())), mode
+
+
+@pytest.mark.parametrize("n_paths,n_stages", [(1, 1), (31, 3), (32, 2), (33, 5), (1000, 8), (4099, 40)])
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+def test_parameter_gradient_kernels_against_einsum(n_paths, n_stages, kind):
+    """tcde_linear_field_param_grads on the tensor cores (3xTF32, variant 0) and on the CUDA cores (variant 1) vs an
+    fp64 einsum over (stage, path): ragged path blocks, zero-weight stages, accumulation onto existing gradients."""
+    from torchcde_b200 import _lib
+    gen = torch.Generator().manual_seed(n_paths + n_stages)
+    hidden, channels, n_rows = 32, 8, 6
+    width = 4 * channels if kind == "cubic" else channels
+    control = torch.randn(n_paths, n_rows, width, generator=gen).to(DEV)
+    z = torch.randn(n_stages, n_paths, hidden, generator=gen).to(DEV)
+    a = torch.randn(n_stages, n_paths, hidden, generator=gen).to(DEV)
+    index = torch.randint(0, n_rows, (n_stages,), generator=gen, dtype=torch.int32)
+    frac = torch.rand(n_stages, generator=gen)
+    weight = torch.randn(n_stages, generator=gen)
+    if n_stages > 2:
+        weight[1] = 0.0
+    c64 = control.double().cpu()
+    want_w = torch.zeros(hidden, channels, hidden, dtype=torch.float64)
+    want_b = torch.zeros(hidden, channels, dtype=torch.float64)
+    for e in range(n_stages):
+        row = c64[:, int(index[e])]
+        f = float(frac[e])
+        if kind == "cubic":
+            dx = row[:, channels:2 * channels] + (row[:, 2 * channels:3 * channels] + row[:, 3 * channels:] * f) * f
+        else:
+            dx = row
+        ae, ze = a[e].double().cpu(), z[e].double().cpu()
+        want_w += float(weight[e]) * torch.einsum("ph,pc,pk->hck", ae, dx, ze)
+        want_b += float(weight[e]) * torch.einsum("ph,pc->hc", ae, dx)
+    want_w, want_b = want_w.reshape(hidden * channels, hidden), want_b.reshape(-1)
+    nbytes = _lib.load().tcde_linear_field_param_grads_scratch_bytes(n_paths, n_stages, channels, hidden)
+    assert nbytes > 0
+    scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=DEV)
+    code = _lib.dtype_code(z.dtype)
+    scale = -0.5
+    index_d, frac_d, weight_d = index.to(DEV), frac.to(DEV), weight.to(DEV)     # kept alive across the launches
+    try:
+        for variant in (0, 1):
+            _lib.call("tcde_set_solve_variant", variant)
+            gw0 = torch.randn(hidden * channels, hidden, generator=gen).to(DEV)
+            gb0 = torch.randn(hidden * channels, generator=gen).to(DEV)
+            gw, gb = gw0.clone(), gb0.clone()
+            _lib.call("tcde_linear_field_param_grads", _lib.ptr(control), _lib.CONTROL_CUBIC if kind == "cubic" else
+                      _lib.CONTROL_LINEAR, n_rows, _lib.ptr(z), _lib.ptr(a), _lib.ptr(index_d),
+                      _lib.ptr(frac_d), _lib.ptr(weight_d), n_stages, _lib.ptr(gw), _lib.ptr(gb),
+                      _lib.ptr(scratch), n_paths, channels, hidden, scale, code, _lib.stream_of(z))
+            torch.cuda.synchronize()
+            for got, want in (((gw - gw0).double().cpu(), scale * want_w), ((gb - gb0).double().cpu(), scale * want_b)):
+                assert float((got - want).abs().max()) <= 3e-5 * max(1.0, float(want.abs().max())), variant
+    finally:
+        _lib.call("tcde_set_solve_variant", 0)

@@ -112,5 +112,13 @@ struct UmmaArgs {
 };
 bool solve_umma_supported(int H, int C);
 int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
+int current_solve_variant();          // tcde_set_solve_variant: 0 auto, 1 CUDA-core kernels, 2 tensor-core kernels
+
+// parameter gradients of a whole backward solve on the tensor cores (param_grad_umma.cu)
+int param_grad_umma_grid(int64_t n_paths, int64_t n_stage_total);
+int param_grad_umma_f32(const float* control, int control_kind, int64_t n_rows, const float* z_stages,
+                        const float* a_stages, const int32_t* stage_index, const float* stage_frac,
+                        const float* stage_weight, int n_stage_total, float* scratch, int64_t n_paths, int grid,
+                        cudaStream_t stream);
 
 }  // namespace tcde

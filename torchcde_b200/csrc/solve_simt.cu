@@ -503,6 +503,7 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
 // ---- tensor-core variant (solve_umma.cu) -------------------------------------------------------
 static long long* g_trace = nullptr;   // profiling aid: device buffer for in-kernel clock stamps (see tcde_set_trace_buffer)
 static int g_solve_variant = 0;     // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
+int current_solve_variant() { return g_solve_variant; }
 
 }  // namespace tcde
 

@@ -374,7 +374,8 @@ extern "C" int tcde_vector_field_linear_vjp(const void* control, int control_kin
 extern "C" int64_t tcde_linear_field_param_grads_scratch_bytes(int64_t n_paths, int64_t n_stages_total, int64_t channels,
                                                               int64_t hidden) {
     if (n_paths < 0 || n_stages_total < 1 || channels != vjp::C || hidden != vjp::H) return -1;
-    return (int64_t)vjp::param_grad_grid(n_paths, n_stages_total) * vjp::kParams * (int64_t)sizeof(float);
+    const int64_t g1 = vjp::param_grad_grid(n_paths, n_stages_total), g2 = param_grad_umma_grid(n_paths, n_stages_total);
+    return (g1 > g2 ? g1 : g2) * vjp::kParams * (int64_t)sizeof(float);
 }
 
 extern "C" int tcde_linear_field_param_grads(const void* control, int control_kind, int64_t n_rows, const void* z_stages,
@@ -394,12 +395,24 @@ extern "C" int tcde_linear_field_param_grads(const void* control, int control_ki
                      reinterpret_cast<uintptr_t>(scratch)) & 15) == 0, "stage buffers and scratch must be 16-byte aligned");
     if (n_paths == 0) return TCDE_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = vjp::param_grad_grid(n_paths, n_stages_total);
-    vjp::param_grad_kernel<<<grid, vjp::kThreads, 0, s>>>((const float*)control, control_kind, n_rows,
-                                                         (const float*)z_stages, (const float*)a_stages, stage_index,
-                                                         (const float*)stage_frac, (const float*)stage_weight,
-                                                         (int)n_stages_total, (float*)scratch, n_paths);
-    TCDE_CHECK_CUDA(cudaGetLastError());
+    int grid;
+    if (current_solve_variant() != 1 && aligned16(control)) {
+        // tensor cores (3xTF32): the product over (stage, path) pairs is one GEMM with generated operands
+        grid = param_grad_umma_grid(n_paths, n_stages_total);
+        const int rc = param_grad_umma_f32((const float*)control, control_kind, n_rows, (const float*)z_stages,
+                                           (const float*)a_stages, stage_index, (const float*)stage_frac,
+                                           (const float*)stage_weight, (int)n_stages_total, (float*)scratch, n_paths,
+                                           grid, s);
+        if (rc != TCDE_OK) return rc;
+    } else {
+        grid = vjp::param_grad_grid(n_paths, n_stages_total);
+        vjp::param_grad_kernel<<<grid, vjp::kThreads, 0, s>>>((const float*)control, control_kind, n_rows,
+                                                             (const float*)z_stages, (const float*)a_stages,
+                                                             stage_index, (const float*)stage_frac,
+                                                             (const float*)stage_weight, (int)n_stages_total,
+                                                             (float*)scratch, n_paths);
+        TCDE_CHECK_CUDA(cudaGetLastError());
+    }
     if (grad_weight || grad_bias) {
         vjp::field_vjp_reduce_kernel<<<(vjp::kParams + 31) / 32, 256, 0, s>>>((const float*)scratch, grid, (float)scale,
                                                                               (float*)grad_weight, (float*)grad_bias);
