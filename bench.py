@@ -388,7 +388,8 @@ def run_gpu_arm(args):
                 t_ms = time_loop(train_step, 2, 1, device) / 2
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {
                     "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "fp32 fma",
-                    "note": "1,020 launches of tcde_vector_field_linear_vjp drive the backward solve; not the headline"}
+                    "note": "backward = two tensor-core solves that keep their stage inputs + one tcgen05 GEMM for dL/dW, dL/db "
+                            "(tcde_cdeint_fixed_linear_stages x2, tcde_linear_field_param_grads); not the headline"}
             except Exception as exc:      # never lose the headline line over the extra
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {"error": repr(exc)}
 
