@@ -387,7 +387,7 @@ def run_gpu_arm(args):
 
                 t_ms = time_loop(train_step, 2, 1, device) / 2
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {
-                    "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "fp32 fma",
+                    "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "tensor (tf32); operand producers today",
                     "note": "backward = two tensor-core solves that keep their stage inputs + one tcgen05 GEMM for dL/dW, dL/db "
                             "(tcde_cdeint_fixed_linear_stages x2, tcde_linear_field_param_grads); not the headline"}
             except Exception as exc:      # never lose the headline line over the extra
