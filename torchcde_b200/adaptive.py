@@ -16,6 +16,12 @@ read (the error ratio), which is also what torchdiffeq pays (``if accept_step``)
 norm is the RMS over the *whole* state tensor, so a batch shares one step sequence
 (SURVEY.md 8e caveat 1).  The vector field is a callable ``field(t_float, y) -> dy``; for the
 linear vector field it is one fused kernel launch (``tcde_vector_field_linear``).
+
+The backward pass of ``adjoint=True`` for the flagship linear field (fp32, hidden 32, channels 8) does not go
+through autograd: a fixed-step backward solve is three launches per segment (``_fused_fixed_backward`` ->
+``solver._kernel_vjp.segment``), an adaptive one gets the field and its vector-Jacobian products from one launch
+per evaluation (``tcde_vector_field_linear_vjp``); the stage combinations and the error ratio of a dopri5
+attempt are single launches too (``tcde_linear_combination`` / ``tcde_error_ratio_sumsq``).
 """
 import ctypes
 
