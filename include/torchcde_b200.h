@@ -198,7 +198,7 @@ TCDE_API int tcde_linear_field_param_grads(const void* control, int control_kind
 
 /* Elementwise pieces of the adaptive driver that stands in for torchdiffeq's dopri5 (the reference's default
  * method, solver.py:226-227): out[i] = base[i] + sum_j coefs[j] * terms[j][i]  (base may be NULL; at most 7
- * terms; `terms` / `coefs` are HOST arrays of device pointers / doubles, read at launch). */
+ * terms; `terms` / `coefs` are HOST arrays of device pointers / doubles, read at launch; out may alias base). */
 TCDE_API int tcde_linear_combination(void* out, const void* base, const void* const* terms, const double* coefs,
                             int n_terms, int64_t n, int dtype, void* stream);
 
