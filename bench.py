@@ -33,6 +33,15 @@ METRIC = "sequences/s for cdeint RK4 (batch=65536,len=256,ch=8,hid=32)"
 BYTES_PER_SEQ = 255 * 3 * CHANNELS * 4 + HIDDEN * 4 + 2 * HIDDEN * 4           # 24,864 B
 FLOPS_PER_SEQ = 255 * (4 * (2 * HIDDEN * HIDDEN * CHANNELS + HIDDEN * CHANNELS + 2 * HIDDEN * CHANNELS + 4 * CHANNELS) + 320)
 HERMITE_BYTES_PER_SEQ = LENGTH * CHANNELS * 4 + (LENGTH - 1) * 4 * CHANNELS * 4   # 40,832 B
+WORKLOAD = ("cdeint rk4 step_size=1 (255 steps, 1020 stage evals), CubicSpline(hermite bdiff coeffs), linear func "
+            "Linear(32,256).view(32,8), batch=65536 per GPU, len=256, ch=8, hid=32, adjoint=False")
+
+
+
+
+def config_for(world):
+    return {"workload": WORKLOAD, "parallelism": "batch-sharded x{}".format(world), "global_batch": world * BATCH,
+            "l2": "inputs (2.1 GB coeffs per GPU) exceed the 126 MB L2; no flush"}
 
 
 _T0 = time.perf_counter()
@@ -157,82 +166,108 @@ def time_loop(fn, steps, warmup, device, dist=None):
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_solve_sample(sample_paths):
-    """The reference's CPU path for the same workload: its op sequence (oracle port) on host cores,
-    with torch's default intra-op thread count (what a reference user gets)."""
+CPU_SAMPLE_PATHS = 8192      # FIXED sample (never calibrated): per-sequence CPU cost depends on the batch size
+
+
+def host_threads():
+    """Threads the CPU arm uses: one per physical core the process may run on (cpu_count // 2 on an SMT-2 host),
+    set explicitly so that torchrun's OMP_NUM_THREADS=1 does not silently turn the arm single-threaded."""
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    return max(1, usable // 2)
+
+
+def cpu_reference_solver(sample_paths):
+    """The reference's OWN ``cdeint`` (unmodified torchcde from /root/reference or oracle/_ref: its
+    ``_check_compatability``, ``_VectorField.forward`` with 63 aten calls and 4 ``item()`` per evaluation,
+    ``CubicSpline.derivative``, output permute) on host cores.  torchdiffeq, which it dispatches to at
+    solver.py:226-227, is not installable offline: ``oracle/odeint_port.py`` stands in for it (kind "_ref+port").
+    Falls back to the streamlined oracle port only if no reference tree is present at all (kind "port")."""
     from oracle import cde_oracle as O
+    from oracle import reference_loader
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(sample_paths, LENGTH, CHANNELS, generator=gen).cumsum(1) / math.sqrt(LENGTH)
     z0 = torch.randn(sample_paths, HIDDEN, generator=gen)
     torch.manual_seed(1)
     lin = torch.nn.Linear(HIDDEN, HIDDEN * CHANNELS)
-    knots = O.knot_times(LENGTH, torch.float32)
     t = torch.tensor([0.0, LENGTH - 1.0])
-    with torch.no_grad():
-        coeffs = O.hermite_backward_difference_coeffs(x)
+    if reference_loader.reference_available():
+        ref = reference_loader.load_reference()
+
+        class ReadmeField(torch.nn.Module):          # README.md:42-49
+            def __init__(self):
+                super().__init__()
+                self.linear = lin
+
+            def forward(self, t, z):
+                return self.linear(z).view(*z.shape[:-1], HIDDEN, CHANNELS)
+
+        func = ReadmeField()
+        with torch.no_grad():
+            coeffs = ref.hermite_cubic_coefficients_with_backward_differences(x)
+            X = ref.CubicSpline(coeffs)
 
         def run():
-            return O.cdeint_linear(coeffs, knots, lin.weight, lin.bias, z0, t, "rk4", 1.0)
-    return run
+            with torch.no_grad():
+                return ref.cdeint(X=X, func=func, z0=z0, t=X.interval, adjoint=False, method="rk4",
+                                  options={"step_size": 1.0})
+        kind = "_ref+port"
+        what = ("the reference's own torchcde.cdeint ({} tree), torchdiffeq replaced by oracle/odeint_port.py"
+                .format(reference_loader.reference_kind()))
+    else:
+        knots = O.knot_times(LENGTH, torch.float32)
+        with torch.no_grad():
+            coeffs = O.hermite_backward_difference_coeffs(x)
+
+        def run():
+            with torch.no_grad():
+                return O.cdeint_linear(coeffs, knots, lin.weight, lin.bias, z0, t, "rk4", 1.0)
+        kind = "port"
+        what = "oracle port of the reference op sequence (no reference tree on this machine)"
+    return run, kind, what
 
 
-def calibrated_sample(budget_s=8.0, lo=256, hi=8192):
-    """Pick the sample size so that one CPU solve takes about ``budget_s`` seconds."""
-    run = cpu_solve_sample(lo)
-    with torch.no_grad():
+def cpu_baseline(reps=4):
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    run, kind, what = cpu_reference_solver(CPU_SAMPLE_PATHS)
+    run()
+    t0 = time.perf_counter()
+    for _ in range(reps):
         run()
-        t0 = time.perf_counter()
-        run()
-        dt = time.perf_counter() - t0
-    n = lo
-    while n * 2 <= hi and dt * (n * 2 / lo) <= budget_s:
-        n *= 2
-    note("cpu calibration: {} paths take {:.2f}s -> sample {}".format(lo, dt, n))
-    return n
-
-
-def cpu_baseline(reps=2):
-    threads = torch.get_num_threads()
-    sample_paths = calibrated_sample()
-    run = cpu_solve_sample(sample_paths)
-    with torch.no_grad():
-        run()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            run()
-        dt = (time.perf_counter() - t0) / reps
-    note("cpu baseline: {} paths in {:.2f}s".format(sample_paths, dt))
-    return {"value": sample_paths / dt, "unit": "sequences/s", "cores": threads, "kind": "port",
-            "host_cpus": os.cpu_count(),
-            "sample": "{} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's order "
-                      "(oracle/cde_oracle.py + oracle/odeint_port.py), mean of {} runs after 1 warm-up, torch's "
-                      "default {} intra-op threads; torchdiffeq itself is not installable here".format(
-                          sample_paths, reps, threads)}
+    dt = (time.perf_counter() - t0) / reps
+    note("cpu baseline ({}): {} paths in {:.2f}s on {} threads".format(kind, CPU_SAMPLE_PATHS, dt, threads))
+    return {"value": CPU_SAMPLE_PATHS / dt, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": kind,
+            "host_cpus": os.cpu_count(), "seconds_per_sample": dt,
+            "sample": "FIXED {} of 65536 paths, full 255 RK4 steps (1020 field evaluations), fp32, {}; mean of {} runs "
+                      "after 1 warm-up, torch.set_num_threads({})".format(CPU_SAMPLE_PATHS, what, reps, threads)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = torch.get_num_threads()
-    sample = calibrated_sample(budget_s=4.0)
-    run = cpu_solve_sample(sample)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            run()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            run()
-        total = time.perf_counter() - t0
-    value = sample * args.steps / total
-    base = {"value": value, "unit": "sequences/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-            "sample": "each step = {} of 65536 paths, full 255 RK4 steps, torch CPU ops in the reference's op "
-                      "order (oracle port; torchdiffeq is not installable offline)".format(sample)}
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    run, kind, what = cpu_reference_solver(CPU_SAMPLE_PATHS)
+    for _ in range(max(1, args.warmup)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    total = time.perf_counter() - t0
+    value = CPU_SAMPLE_PATHS * args.steps / total
+    base = {"value": value, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": kind,
+            "host_cpus": os.cpu_count(),
+            "sample": "each step = FIXED {} of 65536 paths, full 255 RK4 steps, fp32, {}; torch.set_num_threads({})"
+                      .format(CPU_SAMPLE_PATHS, what, threads)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cdeint rk4 step_size=1 CubicSpline(hermite) linear func, sample of "
-                                   "batch=65536 len=256 ch=8 hid=32 on host CPU"},
+            "config": config_for(args.gpus),     # the SAME config as the GPU arm; what was sampled is in cpu_baseline
+            "host": {"threads": threads, "sample_paths_per_step": CPU_SAMPLE_PATHS},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -413,10 +448,7 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cdeint rk4 step_size=1 (255 steps, 1020 stage evals), CubicSpline(hermite bdiff "
-                               "coeffs), linear func Linear(32,256).view(32,8), batch=65536 per GPU, len=256, ch=8, "
-                               "hid=32, adjoint=False", "parallelism": "batch-sharded x{}".format(world),
-                   "global_batch": world * BATCH, "l2": "inputs (2.1 GB coeffs per GPU) exceed the 126 MB L2; no flush"},
+        "config": config_for(world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / e2e_steps,
