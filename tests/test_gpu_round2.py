@@ -1,0 +1,116 @@
+"""Round-2 GPU tests: full-batch parity of the tensor-core solve, the ADVICE r01 regressions and the
+reference-compatibility details added in round 2.  Everything here goes through the C ABI on the device."""
+import math
+
+import pytest
+import torch
+
+import torchcde_b200 as cde
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bench_problem(batch, nan_fraction=0.0, seed=0):
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    L, C, H = 256, 8, 32
+    x = torch.randn(batch, L, C, generator=gen, device=DEV).cumsum(1) / math.sqrt(L)
+    if nan_fraction:
+        hole = torch.rand(x.shape, generator=gen, device=DEV) < nan_fraction
+        hole[:, 0] = False
+        hole[:, -1] = False
+        x = x.masked_fill(hole, float("nan"))
+    z0 = torch.randn(batch, H, generator=gen, device=DEV)
+    torch.manual_seed(1)
+    func = cde.LinearVectorField(H, C).to(DEV)
+    return x, z0, func
+
+
+@pytest.mark.parametrize("nan_fraction", [0.0, 0.3])
+def test_full_batch_fp32_tensor_core_solve_against_fp64_kernel(nan_fraction):
+    """ALL 65,536 paths of BASELINE config 3 (and of a 30 %-NaN config-2 -> config-3 pipeline): the fp32 tcgen05
+    solve against the fp64 CUDA-core solve (itself oracle-checked to 1e-10 in test_gpu_solve.py) on the same
+    fp32-rounded coefficients.  Bar: 1e-5 of the solution scale on every element."""
+    B = 65536
+    x, z0, func = _bench_problem(B, nan_fraction)
+    opts = {"step_size": 1.0}
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
+        assert bool(torch.isfinite(coeffs).all())
+        X = cde.CubicSpline(coeffs)
+        got = cde.cdeint(X, func, z0, X.interval, adjoint=False, method="rk4", options=opts)
+        f64 = cde.LinearVectorField(32, 8, dtype=torch.float64).to(DEV)
+        f64.linear.weight.copy_(func.linear.weight.double())
+        f64.linear.bias.copy_(func.linear.bias.double())
+        worst, scale = 0.0, 0.0
+        for lo in range(0, B, 16384):                      # fp64 coefficients of 16,384 paths: 1 GiB at a time
+            Xd = cde.CubicSpline(coeffs[lo:lo + 16384].double())
+            want = cde.cdeint(Xd, f64, z0[lo:lo + 16384].double(), Xd.interval, adjoint=False, method="rk4", options=opts)
+            worst = max(worst, float((got[lo:lo + 16384].double() - want).abs().max()))
+            scale = max(scale, float(want.abs().max()))
+    assert math.isfinite(scale) and scale > 1.0
+    assert worst <= 1e-5 * scale, "max |fp32 tensor-core - fp64| = {:.3e} at scale {:.3e}".format(worst, scale)
+
+
+def test_large_hidden_linear_field_falls_back_to_the_stage_loop():
+    """hidden=128, channels=8 does not fit the fused kernels; the reference handles it, so must we."""
+    torch.manual_seed(0)
+    x = torch.randn(5, 12, 8, device=DEV).cumsum(1) / 4
+    func = cde.LinearVectorField(128, 8).to(DEV)
+    with torch.no_grad():
+        func.linear.weight.mul_(0.3)
+        X = cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x))
+        z0 = torch.randn(5, 128, device=DEV)
+        out = cde.cdeint(X, func, z0, X.interval, adjoint=False, method="rk4", options={"step_size": 1.0})
+
+        class Opaque:
+            def __call__(self, t, z):
+                return func(t, z)
+
+        want = cde.cdeint(X, Opaque(), z0, X.interval, adjoint=False, method="rk4", options={"step_size": 1.0})
+    assert out.shape == (5, 2, 128)
+    assert torch.allclose(out, want, rtol=1e-5, atol=1e-5)
+
+
+def test_kernel_backed_routes_reject_mismatched_dtype_and_device():
+    """dopri5 / adjoint routes hand raw pointers to the kernels -- a float64 spline with a
+    float32 state, or a field left on the CPU, must raise a clean RuntimeError like the reference's torch ops do."""
+    torch.manual_seed(0)
+    x = torch.randn(4, 9, 8, device=DEV).cumsum(1) / 3
+    with torch.no_grad():
+        coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
+    func = cde.LinearVectorField(32, 8).to(DEV)
+    z0 = torch.randn(4, 32, device=DEV)
+    X64 = cde.CubicSpline(coeffs.double())
+    for kwargs in ({"method": "rk4", "options": {"step_size": 1.0}}, {}):           # fixed step and the default dopri5
+        with pytest.raises(RuntimeError, match="must match"):
+            with torch.no_grad():
+                cde.cdeint(X64, func, z0, X64.interval, adjoint=False, **kwargs)
+        with pytest.raises(RuntimeError):
+            with torch.no_grad():
+                cde.cdeint(cde.CubicSpline(coeffs), cde.LinearVectorField(32, 8), z0, X64.interval, adjoint=False, **kwargs)
+    zg = z0.clone().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="must match"):
+        cde.cdeint(X64, func, zg, X64.interval, adjoint=True, method="rk4", options={"step_size": 1.0})
+    # the device is still healthy (no sticky error): a correct call works
+    with torch.no_grad():
+        X = cde.CubicSpline(coeffs)
+        out = cde.cdeint(X, func, z0, X.interval, adjoint=False, method="rk4", options={"step_size": 1.0})
+    assert bool(torch.isfinite(out).all())
+
+
+def test_linear_interpolation_state_dict_matches_the_reference_keys():
+    """reference checkpoints of LinearInterpolation hold ``_t``, ``_coeffs``, ``_derivs``
+    (interpolation_linear.py:191-193) and must load with strict=True; slopes follow a load."""
+    torch.manual_seed(0)
+    a = torch.randn(3, 7, 2, device=DEV)
+    b = torch.randn(3, 7, 2, device=DEV)
+    Xa, Xb = cde.LinearInterpolation(a), cde.LinearInterpolation(b)
+    assert sorted(Xa.state_dict().keys()) == ["_coeffs", "_derivs", "_t"]
+    want = (a[:, 1:] - a[:, :-1]) / 1.0
+    assert torch.equal(Xa._derivs, want)
+    Xb.load_state_dict(Xa.state_dict(), strict=True)
+    assert torch.equal(Xb._derivs, want) and torch.equal(Xb.derivative(torch.tensor(2.5, device=DEV)), want[:, 2])
+    # a module built on the CPU and moved afterwards carries the same slopes
+    Xc = cde.LinearInterpolation(a.cpu()).to(DEV)
+    assert torch.equal(Xc._derivs, want)

@@ -1,10 +1,10 @@
 """GPU parity, hot path (ii): spline evaluation and the fused fixed-step solve through the C ABI.
 
 Tolerances.  Interval indices: bit exact.  Spline evaluation: bit exact.  The solve: fp64 to
-1e-10 relative; fp32 to rtol 1e-4 (the north_star's tolerance) with atol 1e-4 x the solution
-scale -- the reference's own addmm/bmm reduction order is not reproducible, so two fp32 runs of
-the *reference* on different hardware differ by about the same amount (fp32 vs fp64
-of one algorithm ~1e-6 median)."""
+1e-10 relative; fp32 to 1e-5 of the solution scale (10x inside the north_star's rtol 1e-4; the
+observed error is ~5e-7 of scale) -- the reference's own addmm/bmm reduction order
+is not reproducible, so two fp32 runs of the *reference* on different hardware differ by ~1e-6
+(fp32 vs fp64 of one algorithm ~1e-6 median)."""
 import math
 
 import pytest
@@ -22,7 +22,7 @@ def _assert_close(got, want, dtype):
     want = want.to(torch.float64)
     got = got.detach().cpu().to(torch.float64)
     scale = max(1.0, float(want.abs().max()))
-    rtol, atol = (1e-4, 1e-4 * scale) if dtype == torch.float32 else (1e-10, 1e-10 * scale)
+    rtol, atol = (1e-5, 1e-5 * scale) if dtype == torch.float32 else (1e-10, 1e-10 * scale)
     err = (got - want).abs()
     assert bool((err <= atol + rtol * want.abs()).all()), "max err {:.3e} at scale {:.3e}".format(float(err.max()), scale)
 

@@ -103,7 +103,7 @@ def test_schedule_knot_semantics_and_reversal():
 
 def test_linear_field_recognition():
     z0 = torch.randn(4, 3)
-    t0 = torch.tensor(0.0)
+    t0 = [0.0, 1.0]                  # the integration interval: the probe picks its own non-degenerate times in it
     good = cde.LinearVectorField(3, 2)
     assert solver.linear_field_of(good, z0, 2, t0)[0] is good.linear.weight
     assert solver.linear_field_of(good, z0, 5, t0) is None            # wrong channel count
@@ -128,6 +128,20 @@ def test_linear_field_recognition():
     assert solver.linear_field_of(WithTanh(), z0, 2, t0) is None
     assert solver.linear_field_of(Transposed(), z0, 2, t0) is None
     assert solver.linear_field_of(lambda t, z: z, z0, 2, t0) is None
+
+    # modules that agree with their nn.Linear only at a degenerate probe point (t = 0, z = 0)
+    class DecaysInTime(Readme):
+        def forward(self, t, z):
+            return self.linear(z).view(4, 3, 2) * torch.exp(-t)
+
+    class TanhInside(Readme):
+        def forward(self, t, z):
+            return self.linear(torch.tanh(z)).view(4, 3, 2)
+
+    zeros = torch.zeros(4, 3)
+    assert solver.linear_field_of(DecaysInTime(), zeros, 2, [0.0, 1.0]) is None
+    assert solver.linear_field_of(TanhInside(), zeros, 2, [0.0, 1.0]) is None
+    assert solver.linear_field_of(Readme(), zeros, 2, [0.0, 1.0]) is not None
 
 
 def test_scalar_host_locator_equals_the_tensor_one():

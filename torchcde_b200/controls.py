@@ -141,24 +141,23 @@ class LinearInterpolation(InterpolationBase):
         if t is None:
             t = torch.linspace(0, coeffs.size(-2) - 1, coeffs.size(-2), dtype=coeffs.dtype, device=coeffs.device)
 
+        # slopes per interval, precomputed and registered like the reference (interpolation_linear.py:189-193:
+        # state_dict keys ``_t``, ``_coeffs``, ``_derivs``); on the GPU they come from the evaluation kernel (the same
+        # ``(x[i+1] - x[i]) / (t[i+1] - t[i])``, bit-identical); a module built from CPU tensors (to be moved with
+        # ``.to(device)`` before use) forms them with the reference's own two torch ops
+        if coeffs.is_cuda:
+            n = coeffs.size(-2) - 1
+            index = torch.arange(n, device=coeffs.device)
+            frac = torch.zeros(n, dtype=coeffs.dtype, device=coeffs.device)
+            knots = t.detach().to(device=coeffs.device, dtype=coeffs.dtype).contiguous()
+            derivs = _eval_kernel(coeffs.detach(), knots, coeffs.size(-2), coeffs.size(-1), index, frac,
+                                  _lib.CONTROL_LINEAR, True)
+        else:
+            derivs = (coeffs[..., 1:, :] - coeffs[..., :-1, :]) / (t[1:] - t[:-1]).unsqueeze(-1)
+
         self.register_buffer('_t', t)
         self.register_buffer('_coeffs', coeffs)
-        self._derivs_cache = None
-
-    @property
-    def _derivs(self):
-        """Slopes per interval (interpolation_linear.py:189), formed on first use by the kernel
-        (the same ``(x[i+1] - x[i]) / (t[i+1] - t[i])``, bit-identical) and cached."""
-        cached = self._derivs_cache
-        if cached is None or cached.device != self._coeffs.device or cached.dtype != self._coeffs.dtype:
-            n = self._coeffs.size(-2) - 1
-            index = torch.arange(n, device=self._coeffs.device)
-            frac = torch.zeros(n, dtype=self._coeffs.dtype, device=self._coeffs.device)
-            knots = self._t.detach().to(self._coeffs.dtype).contiguous()
-            cached = _eval_kernel(self._coeffs.detach(), knots, self._coeffs.size(-2), self._coeffs.size(-1), index,
-                                  frac, _lib.CONTROL_LINEAR, True)
-            self._derivs_cache = cached
-        return cached
+        self.register_buffer('_derivs', derivs)
 
     @property
     def grid_points(self):

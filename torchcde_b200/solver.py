@@ -57,12 +57,14 @@ def _single_linear(func):
     return mods[0]
 
 
-def linear_field_of(func, z0, channels, t0):
+def linear_field_of(func, z0, channels, times):
     """Return ``(weight, bias)`` if ``func(t, z)`` is exactly ``Linear(H, H*C)(z).view(..., H, C)``.
 
     ``LinearVectorField`` is trusted; any other module made of a single ``nn.Linear`` of the
-    right shape is *probed* on a handful of paths and must reproduce the linear map bit for
-    bit (so a module that adds an activation is never mistaken for a linear field)."""
+    right shape is *probed*: it must reproduce the linear map bit for bit on random states at
+    several distinct times of the integration interval (so a module that adds an activation, or
+    scales by a function of ``t``, is never mistaken for a linear field -- probing at ``(t[0], z0)``
+    alone is degenerate for ``z0 == 0`` or ``t[0] in {0, 1}``)."""
     hidden = z0.size(-1)
     if isinstance(func, LinearVectorField):
         lin = func.linear
@@ -77,7 +79,7 @@ def linear_field_of(func, z0, channels, t0):
     except TypeError:
         known = None
     if known is None:
-        known = _probe(func, lin, z0, channels, t0)
+        known = _probe(func, lin, z0, channels, times)
         try:
             _recognised[func] = known
         except TypeError:
@@ -85,24 +87,50 @@ def linear_field_of(func, z0, channels, t0):
     return (lin.weight, lin.bias) if known else None
 
 
-def _probe(func, lin, z0, channels, t0):
+def _probe(func, lin, z0, channels, times):
+    """Bit-exact comparison of ``func`` with its ``nn.Linear`` on random (non-degenerate) states of z0's own
+    shape (user modules may hard-code the batch size) at four distinct times, none of them 0 or 1."""
     hidden = z0.size(-1)
+    if z0.numel() * channels > (1 << 27):
+        # too large to probe at full shape: only the explicit LinearVectorField gets the fused kernel
+        return False
+    lo, hi = float(times[0]), float(times[-1])
+    span = hi - lo if hi != lo else 1.0
+    probe_times = [lo + 0.6180339887 * span, lo + 0.2718281828 * span + 0.0137, hi + 0.5772156649, lo - 0.4142135624]
+    gen = torch.Generator(device=z0.device).manual_seed(0x5eed)
     with torch.no_grad():
-        flat = z0.detach().reshape(-1, hidden)
-        small = z0.detach() if flat.size(0) * hidden * channels <= (1 << 22) else None
-        candidates = [small] if small is not None else [z0.detach()[tuple(slice(0, 1) for _ in z0.shape[:-1])]]
-        for zp in candidates:
+        for i, tv in enumerate(probe_times):
+            zp = torch.randn(z0.shape, generator=gen, device=z0.device, dtype=z0.dtype) * (0.5 + 1.3 * i) + 0.21 * i
+            tp = torch.tensor(tv, dtype=z0.dtype, device=z0.device)
             try:
-                got = func(t0, zp)
+                got = func(tp, zp)
             except Exception:
-                warnings.warn("torchcde_b200.cdeint: `func` looks like a single nn.Linear but could not be probed on "
-                              "a slice of z0 (does it hard-code the batch size?). Falling back to the generic stage "
-                              "loop; use torchcde_b200.LinearVectorField to get the fused kernel.")
+                warnings.warn("torchcde_b200.cdeint: `func` looks like a single nn.Linear but could not be probed. "
+                              "Falling back to the generic stage loop; use torchcde_b200.LinearVectorField to get the "
+                              "fused kernel.")
                 return False
             want = torch.nn.functional.linear(zp, lin.weight, lin.bias).view(*zp.shape[:-1], hidden, channels)
-            if not (isinstance(got, torch.Tensor) and got.shape == want.shape and torch.equal(got, want)):
+            if not (isinstance(got, torch.Tensor) and got.shape == want.shape and got.dtype == want.dtype
+                    and torch.equal(got, want)):
                 return False
     return True
+
+
+def _check_linear_problem(control, weight, bias, z0):
+    """One validator for every kernel-backed route (fused solve, kernel field, kernel vjp): the control's
+    coefficients, the weight and the bias must share z0's dtype and CUDA device -- the kernels receive raw
+    pointers, so a mismatch would be reinterpreted memory, not an exception (the reference raises a dtype /
+    device RuntimeError from its torch ops in the same situations)."""
+    _lib.require_cuda(z0, control, weight, bias)
+    for name, ten in (("the control's coefficients", control), ("func's weight", weight), ("func's bias", bias)):
+        if ten is None:
+            continue
+        if ten.dtype != z0.dtype:
+            raise RuntimeError("torchcde_b200.cdeint: z0 is {} but {} are {}; they must match."
+                               .format(z0.dtype, name, ten.dtype))
+        if ten.device != z0.device:
+            raise RuntimeError("torchcde_b200.cdeint: z0 is on {} but {} are on {}; they must be on the same device."
+                               .format(z0.device, name, ten.device))
 
 
 # ------------------------------------------------------------------------------- validation
@@ -159,11 +187,7 @@ def _fused_solve(X, weight, bias, z0, t, method, step_size):
     dtype = z0.dtype
     code = _lib.dtype_code(dtype)
     control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
-    for name, ten in (("the control's coefficients", control), ("func's weight", weight)):
-        if ten.dtype != dtype:
-            raise RuntimeError("torchcde_b200.cdeint: z0 is {} but {} are {}; they must match."
-                               .format(dtype, name, ten.dtype))
-    _lib.require_cuda(z0, control, weight)
+    _check_linear_problem(control, weight, bias, z0)
     with torch.cuda.device(z0.device):
         control = control.detach().reshape(-1, control.size(-2), control.size(-1))
         if not control.is_contiguous():
@@ -287,6 +311,7 @@ def _kernel_field(X, weight, bias, z0):
     hidden = z0.size(-1)
     code = _lib.dtype_code(z0.dtype)
     control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+    _check_linear_problem(control, weight, bias, z0)
     control = control.detach().reshape(-1, control.size(-2), control.size(-1)).contiguous()
     w = weight.detach().contiguous()
     b = bias.detach().contiguous() if bias is not None else torch.zeros(hidden * channels, dtype=z0.dtype,
@@ -322,7 +347,9 @@ def _kernel_vjp(X, weight, bias, z0, params):
             roles.append("b")
         else:
             return None                       # a parameter that is not the linear map: autograd knows how
-    if z0.dtype != torch.float32 or weight.dtype != torch.float32:
+    control_check = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+    _check_linear_problem(control_check, weight, bias, z0)
+    if z0.dtype != torch.float32:
         return None
     n_paths = z0.numel() // hidden
     scratch_bytes = _lib.load().tcde_vector_field_linear_vjp_scratch_bytes(n_paths, channels, hidden)
@@ -462,8 +489,9 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
     Supported in this round: ``backend="torchdiffeq"`` semantics with the fixed-step methods
     ``euler``, ``midpoint`` and ``rk4`` (torchdiffeq's 3/8 rule).  With a ``CubicSpline`` or
     ``LinearInterpolation`` control and a linear ``func`` (``LinearVectorField`` or any module
-    that is exactly one ``nn.Linear`` + ``view``) the solve is one fused CUDA kernel; gradients
-    are served by the differentiable generic stage loop.
+    that is exactly one ``nn.Linear`` + ``view``) the solve is one fused CUDA kernel.  Gradients:
+    ``adjoint=True`` runs this package's continuous-adjoint backward (fused kernels for the linear
+    field), ``adjoint=False`` backpropagates through the differentiable generic stage loop.
     """
     # Reduce the default values for the tolerances because CDEs are difficult to solve with the default high tolerances.
     if 'atol' not in kwargs:
@@ -503,6 +531,9 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
 
     is_prod = hasattr(func, 'prod')
     sig = _control_signature(X)
+    # the ONE host read of the output times (a device->host copy only if the caller put ``t`` on the GPU; the
+    # schedule -- grid, interval index of every stage -- is host arithmetic, like torchdiffeq's own grid construction)
+    times = [float(v) for v in t.detach().cpu().tolist()]
 
     if adjoint and 'adjoint_params' not in kwargs:
         for buffer in X.buffers():
@@ -524,8 +555,7 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
     field_params = None
     if sig is not None and not is_prod:
         kind, batch, channels, _ = sig
-        t0 = t[0].detach().to(z0.dtype) if t.numel() else t
-        field_params = linear_field_of(func, z0, channels, t0)
+        field_params = linear_field_of(func, z0, channels, times) if times else None
     if field_params is not None:
         # shapes are checked from metadata: nothing is evaluated on the batch
         _shape_error_forward(batch + (channels,), tuple(z0.shape[:-1]) + (z0.size(-1), channels), z0)
@@ -556,7 +586,6 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
     wants_grad = torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad
                                                  for x in differentiable)
 
-    times = [float(v) for v in t.detach().cpu().tolist()]
     flipped = len(times) > 1 and times[0] > times[1]
     if flipped:
         times = [-v for v in times]
@@ -582,8 +611,13 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
         """Outputs only, time first, by the fastest route."""
         if method in FIXED_METHODS:
             if field_params is not None:
-                out = _fused_solve(X, field_params[0], field_params[1], y0, t, method, step_size)
-                return out.movedim(-2, 0)
+                try:
+                    out = _fused_solve(X, field_params[0], field_params[1], y0, t, method, step_size)
+                    return out.movedim(-2, 0)
+                except NotImplementedError:
+                    # a shape the fused kernels are not built for (e.g. hidden * channels * hidden beyond the
+                    # shared-memory budget of the CUDA-core kernel): this package's own stage loop takes any shape
+                    pass
             return _generic_solve(X, func, y0, t, method, step_size, is_prod, sig is not None).movedim(-2, 0)
         return adaptive.odeint_dopri5(fast_field(), y0, times, rtol, atol, options)[0]
 
