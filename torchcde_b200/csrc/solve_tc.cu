@@ -1,0 +1,520 @@
+// Hot path (ii), round 2: the fused fixed-step CDE solve on tcgen05 with the Runge-Kutta state in registers.
+//
+// What changed against solve_umma.cu (round 1, kept as variant 2) and why -- profiles/r01_umma_trace.txt showed one
+// tile-stage as a 4,065-cycle serial chain of which only 1,664 are tensor work (13 MMAs x 128 cycles: the issue loop
+// finishes after ~1,330 because the MMA queue holds the last three), so two ping-ponging tiles kept the pipe 82 % busy:
+//   * the slopes k1 and k2 (+k3) never leave registers (one CTA per SM: the register file is there to be used): the
+//     64 LDS + 32-64 STS per thread and stage of the old "park" and their latency are gone;
+//   * MODE 1 halves the tensor work itself: operands are split into TWO FP16 pieces instead of two TF32 pieces.  An
+//     FP16 MMA carries K = 16 per instruction at the cycle cost of a K = 8 TF32 one, so the three partial products
+//     z_lo.W_hi + z_hi.W_lo + z_hi.W_hi are 6 MMAs instead of 12 (+1 for the bias in both modes).  FP16 has the same
+//     11-bit significand as TF32 (hi + lo = 22 bits, error ~2^-22 like 3xTF32) but only 5 exponent bits, so every
+//     path's row is scaled by its own power of two (exact) so that max(|z_k|, bias floor) lands in [2^13, 2^14); the
+//     weights get one global power of two; elements more than 2^-27 below the row maximum lose relative -- not
+//     absolute -- precision, which is what a dot product needs.  The scale is undone for free by folding its inverse
+//     into the path's dX/dt before the contraction.  hi | lo of a row share ONE 128-byte swizzled A row (K = 64).
+//
+//   * no dedicated issuer warp: 9 warps are allocated like 12 (168 registers per thread), 8 warps get 255.  Lane 0 of a
+//     tile's first warp issues the tile's MMAs as soon as the tile's 128 rows have arrived on a_ready[t].
+//
+// CTA anatomy: two tiles of 128 paths, thread = path (256 threads); accumulators [128 x 256] fp32 per tile in TMEM (all
+// 512 columns); a_ready[t] (128 arrivals) / d_ready[t] (tcgen05.commit) mbarriers.
+#include <cuda_fp16.h>
+
+#include "umma.cuh"
+
+namespace tcde {
+
+namespace tc {
+
+using namespace umma;
+
+constexpr int kH = 32;
+constexpr int kC = 8;
+constexpr int kN = kH * kC;       // 256 accumulator columns per tile
+constexpr int kTile = 128;
+constexpr int kTiles = 2;
+constexpr int kThreads = kTile * kTiles;
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {          // (lo, hi) -> f16x2, round to nearest even
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack_h2(uint32_t h, float& lo, float& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
+}
+__device__ __forceinline__ int exponent_of(float m) { return (int)((__float_as_uint(m) >> 23) & 0xFFu); }   // biased
+__device__ __forceinline__ float pow2_biased(int e) { return __uint_as_float((uint32_t)e << 23); }          // 2^(e-127)
+
+// shared-memory map (bytes).  MODE 0: TF32 hi / lo tiles (K = 32 floats = one 128-byte row each);
+// MODE 1: one FP16 tile per operand, row = [hi(32) | lo(32)] halves = 128 bytes.
+template <int MODE> struct Smem {
+    static constexpr int b_bytes = (MODE == 0 ? 2 : 1) * kN * 128;
+    static constexpr int a_tile_bytes = (MODE == 0 ? 2 : 1) * kTile * 128;          // per tile: hi (+ lo tile in MODE 0)
+    static constexpr int b = 0;
+    static constexpr int a = b + b_bytes;
+    static constexpr int raw = a + kTiles * a_tile_bytes;                            // [kTiles][6][kTile] float4
+    static constexpr int b_aug = raw + kTiles * 6 * kTile * 16;                      // N rows x 32 B (no swizzle, K-major)
+    static constexpr int a_aug = b_aug + kN * 32;                                    // [kTiles][128 rows x 32 B] (MODE 0: one 8-row group)
+    static constexpr int red = a_aug + kTiles * kTile * 32;                          // 64 floats of reduction scratch
+    static constexpr int bars = red + 256;
+    static constexpr int total = bars + 64;
+};
+
+// byte offset of (row, 16-byte chunk) in a K-major no-swizzle tile of 32-byte rows: 8-row groups 256 B apart (SBO),
+// the two K chunks 128 B apart (LBO), rows 16 B apart
+__device__ __forceinline__ uint32_t aug_off(int row, int chunk) { return (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16); }
+
+template <int MODE, bool TRACE, bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a) {
+    using S = Smem<MODE>;
+    using E = exact<float>;
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+    uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
+    uint64_t* d_ready = a_ready + kTiles;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
+    float* red = reinterpret_cast<float*>(smem + S::red);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int64_t cta_path0 = (int64_t)blockIdx.x * (kTile * kTiles);
+    const int total = a.n_steps * a.n_stages;
+
+    // ---- one-time setup: operand B (the weights, split) and the bias K-block -------------------------------------
+    float w_scale = 1.f, inv_w_scale = 1.f, beta = 0.f;       // MODE 1: global power-of-two scales
+    if (MODE == 1) {
+        float wmax = 0.f, bmax = 0.f;
+        for (int e = tid; e < kN * kH; e += kThreads) wmax = fmaxf(wmax, fabsf(a.weight[e]));
+        for (int e = tid; e < kN; e += kThreads) bmax = fmaxf(bmax, fabsf(a.bias[e]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+            bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+        }
+        if ((tid & 31) == 0) { red[warp] = wmax; red[16 + warp] = bmax; }
+        __syncthreads();
+        wmax = 0.f; bmax = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) { wmax = fmaxf(wmax, red[w]); bmax = fmaxf(bmax, red[16 + w]); }
+        // exponents clamped so that every derived power of two is a normal fp32 number; an all-zero weight takes the
+        // bias's exponent (the product is then the bias alone)
+        const int eb = min(max(exponent_of(bmax), 40), 215);
+        const int ew = (wmax > 0.f) ? min(max(exponent_of(wmax), 40), 215) : (bmax > 0.f ? eb : 127);
+        w_scale = pow2_biased(127 + 13 - (ew - 127));                                // max |W| * w_scale in [2^13, 2^14)
+        inv_w_scale = pow2_biased(127 - 13 + (ew - 127));
+        if (bmax > 0.f) beta = pow2_biased(min(max(127 + eb - ew, 2), 250));         // 2^(ex(bmax) - ex(wmax))
+    }
+    if (MODE == 0) {
+        float* b_hi = reinterpret_cast<float*>(smem + S::b);
+        float* b_lo = b_hi + kN * 32;
+        for (int e = tid; e < kN * kH; e += kThreads) {
+            const int n = e >> 5, k = e & 31;
+            const float w = a.weight[e];                     // weight[n][k], n = h*C + c
+            const float hi = tf32_hi(w);
+            b_hi[swz(n, k)] = hi;
+            b_lo[swz(n, k)] = w - hi;
+        }
+        float* a_aug = reinterpret_cast<float*>(smem + S::a_aug);
+        float* b_aug = reinterpret_cast<float*>(smem + S::b_aug);
+        for (int e = tid; e < 8 * 8; e += kThreads) {
+            const int row = e >> 3, k = e & 7;
+            a_aug[(k >> 2) * 32 + row * 4 + (k & 3)] = (k < 2) ? 1.f : 0.f;         // (1, 1, 0...): SBO = 0 serves all rows
+        }
+        for (int e = tid; e < kN * 8; e += kThreads) {
+            const int row = e >> 3, k = e & 7;
+            const float bv = a.bias[row];
+            const float hi = tf32_hi(bv);
+            b_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k == 0) ? hi : (k == 1) ? (bv - hi) : 0.f;
+        }
+    } else {
+        __half* bt = reinterpret_cast<__half*>(smem + S::b);
+        for (int e = tid; e < kN * kH; e += kThreads) {
+            const int n = e >> 5, k = e & 31;
+            const float w = a.weight[e] * w_scale;
+            const __half hi = __float2half_rn(w);
+            const __half lo = __float2half_rn(w - __half2float(hi));
+            // row n = 128 bytes: halves 0..31 = hi, 32..63 = lo; 16-byte chunk c (8 halves) sits at c ^ (n & 7)
+            bt[n * 64 + ((((k >> 3)) ^ (n & 7)) << 3) + (k & 7)] = hi;
+            bt[n * 64 + ((((k >> 3) + 4) ^ (n & 7)) << 3) + (k & 7)] = lo;
+        }
+        unsigned char* b_aug = smem + S::b_aug;
+        unsigned char* a_aug = smem + S::a_aug;
+        const float bias_scale = (beta > 0.f) ? w_scale / beta : 0.f;                // bias * w_scale / beta in [2^13, 2^14)
+        for (int row = tid; row < kN; row += kThreads) {
+            const float bv = a.bias[row] * bias_scale;
+            const __half hi = __float2half_rn(bv);
+            const __half lo = __float2half_rn(bv - __half2float(hi));
+            uint4 c0 = make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(b_aug + aug_off(row, 0)) = c0;
+            *reinterpret_cast<uint4*>(b_aug + aug_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int e = tid; e < kTiles * kTile * 2; e += kThreads)                     // per-row scale goes to k = 0, 1 each stage
+            *reinterpret_cast<uint4*>(a_aug + (e >> 8) * (kTile * 32) + aug_off((e >> 1) & 127, e & 1)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        for (int t = 0; t < kTiles; ++t) {
+            mbar_init(&a_ready[t], kTile);
+            mbar_init(&d_ready[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    bool tile_live[kTiles];
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
+
+    {
+        // ================================ row threads =========================================
+        const int t = warp >> 2;                          // tile of this thread
+        const int r = tid & (kTile - 1);                  // row (path) within the tile
+        const int64_t path = cta_path0 + (int64_t)t * kTile + r;
+        const bool live = path < a.n_paths;
+        const int64_t lpath = live ? path : a.n_paths - 1;
+        if (tile_live[t]) {
+            unsigned char* a_tile = smem + S::a + t * S::a_tile_bytes;
+            unsigned char* a_aug = smem + S::a_aug + t * kTile * 32;
+            float4* raw = reinterpret_cast<float4*>(smem + S::raw) + (size_t)t * 6 * kTile + r;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * kN);
+            const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
+            const int row_stride = cubic ? 4 * kC : kC;
+            const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? kC : 0);
+            const float sign = (a.sign < 0.f) ? -1.f : 1.f;
+            float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
+
+            // ---- the tile's MMAs, issued by lane 0 of the tile's first warp once all 128 rows of the operand are in place
+            // instruction descriptor: D = F32 (bit 4), A/B format (bits 7 / 10: 2 = TF32, 0 = F16), N >> 3 (bit 17), M >> 4 (bit 24)
+            constexpr uint32_t fmt = (MODE == 0) ? 2u : 0u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+            const bool issuer_warp = (warp & 3) == 0;
+            uint32_t phase_a = 0;
+            auto issue_stage = [&](int st) {
+                mbar_wait(&a_ready[t], phase_a);
+                phase_a ^= 1;
+                tc_fence_after();
+                if ((tid & 31) == 0) {
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+                    const uint64_t db = make_desc(smem + S::b);
+                    // K-major no-swizzle descriptors: LBO = 128 B (next 16 bytes of K), SBO = 256 B (next 8 rows), version 1
+                    const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+                    const uint32_t d = tmem_base + (uint32_t)(t * kN);
+                    if (MODE == 0) {
+                        const uint64_t db_lo = make_desc(smem + S::b + kN * 128);
+                        const uint64_t dah = make_desc(a_tile);
+                        const uint64_t dal = make_desc(a_tile + kTile * 128);
+                        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (0ull << 32) | (1ull << 46);
+                        // small terms first; each K block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, db + 2 * kb, idesc, kb > 0);
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db_lo + 2 * kb, idesc, 1);
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db + 2 * kb, idesc, 1);
+                        mma_tf32(d, da_aug, db_aug, idesc, 1);                // + bias (1 * bias_hi + 1 * bias_lo)
+                    } else {
+                        const uint64_t da = make_desc(a_tile);
+                        const uint64_t da_aug = (uint64_t)((smem_u32(a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+                        // K block = 16 halves = 32 bytes = +2; A row = [hi: blocks 0,1 | lo: blocks 2,3], B row likewise
+                        mma_f16(d, da + 4, db + 0, idesc, 0);                 // z_lo . W_hi
+                        mma_f16(d, da + 6, db + 2, idesc, 1);
+                        mma_f16(d, da + 0, db + 4, idesc, 1);                 // z_hi . W_lo
+                        mma_f16(d, da + 2, db + 6, idesc, 1);
+                        mma_f16(d, da + 0, db + 0, idesc, 1);                 // z_hi . W_hi
+                        mma_f16(d, da + 2, db + 2, idesc, 1);
+                        mma_f16(d, da_aug, db_aug, idesc, 1);                 // + row_scale * bias
+                    }
+                    mma_commit(&d_ready[t]);
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
+                }
+                __syncwarp();
+            };
+
+            auto fetch_row = [&](int idx) {               // (b | 2c | 3d) of interval idx -> raw[0..5]
+                const float* src = crow + (int64_t)idx * row_stride;
+                const int parts = cubic ? 6 : 2;
+                for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
+                cp_async_commit();
+            };
+            auto write_a = [&](const float* z, int stage_no) {   // next stage input -> split operand rows
+                if (DUMP && live) {                       // ... and, for the adjoint, to the trajectory in HBM
+                    float4* dst = reinterpret_cast<float4*>(a.stage_dump + ((int64_t)stage_no * a.n_paths + path) * kH);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
+                }
+                if (MODE == 0) {
+                    float* a_hi = reinterpret_cast<float*>(a_tile);
+                    float* a_lo = a_hi + kTile * 32;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 hi, lo;
+                        hi.x = tf32_hi(z[4 * c4 + 0]); hi.y = tf32_hi(z[4 * c4 + 1]);
+                        hi.z = tf32_hi(z[4 * c4 + 2]); hi.w = tf32_hi(z[4 * c4 + 3]);
+                        upk(sub2(pk(z[4 * c4 + 0], z[4 * c4 + 1]), pk(hi.x, hi.y)), lo.x, lo.y);
+                        upk(sub2(pk(z[4 * c4 + 2], z[4 * c4 + 3]), pk(hi.z, hi.w)), lo.z, lo.w);
+                        const uint32_t off = (uint32_t)r * 32u + (uint32_t)((c4 ^ (r & 7)) << 2);
+                        *reinterpret_cast<float4*>(a_hi + off) = hi;
+                        *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    }
+                } else {
+                    // the path's own power of two: max(|z_k|, bias floor) * s in [2^13, 2^14)
+                    float m = beta;
+#pragma unroll
+                    for (int k = 0; k < kH; ++k) m = fmaxf(m, fabsf(z[k]));
+                    const int e = min(max(exponent_of(m), 30), 224);
+                    const float s = pow2_biased(127 + 13 - (e - 127));
+                    inv_scale = pow2_biased(127 - 13 + (e - 127)) * inv_w_scale;
+                    const f2 s2 = pk(s, s);
+                    uint32_t hi_h[16], lo_h[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const f2 sc = mul2(pk(z[2 * j], z[2 * j + 1]), s2);
+                        float s0, s1, h0, h1, l0, l1;
+                        upk(sc, s0, s1);
+                        hi_h[j] = pack_h2(s0, s1);
+                        unpack_h2(hi_h[j], h0, h1);
+                        upk(sub2(sc, pk(h0, h1)), l0, l1);
+                        lo_h[j] = pack_h2(l0, l1);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        *reinterpret_cast<uint4*>(a_tile + r * 128 + ((c ^ (r & 7)) << 4)) =
+                            make_uint4(hi_h[4 * c], hi_h[4 * c + 1], hi_h[4 * c + 2], hi_h[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(a_tile + r * 128 + (((c + 4) ^ (r & 7)) << 4)) =
+                            make_uint4(lo_h[4 * c], lo_h[4 * c + 1], lo_h[4 * c + 2], lo_h[4 * c + 3]);
+                    }
+                    const float sb = s * beta;            // <= 2^13 by construction; exact, flushes to 0 far below the row maximum
+                    *reinterpret_cast<uint32_t*>(a_aug + aug_off(r, 0)) = pack_h2(sb, sb);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&a_ready[t]);
+            };
+            auto write_out = [&](int j, const float* v) {
+                if (!live) return;
+                float4* dst = reinterpret_cast<float4*>(a.out + (path * a.n_out + j) * kH);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            };
+
+            float y[kH], k1[kH], s23[kH];
+            {
+                const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 v = zp[c4];
+                    y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int h = 0; h < kH; ++h) { k1[h] = 0.f; s23[h] = 0.f; }
+            }
+            int jn = 0;
+            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
+            while (jn < a.n_out && next_out < 0) {
+                write_out(jn, y);
+                ++jn;
+                next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+            }
+            fetch_row(a.stage_index[0]);
+            write_a(y, 0);
+            if (issuer_warp) issue_stage(0);
+
+            const float third = (float)(1.0 / 3.0);
+            int step = 0, sub = 0;
+            float dt = a.step_dt[0];
+            float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
+            float frac0 = a.stage_frac[0];                        // this stage's fraction
+            int idx1 = (total > 1) ? a.stage_index[1] : 0;        // next stage's schedule entry
+            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;
+            uint32_t phase = 0;
+            for (int st = 0; st < total; ++st) {
+                const bool more = st + 1 < total;
+                // ---- in the MMA's shadow: dX/dt from the prefetched row (interpolation_cubic.py:331-336), times the
+                //      sign of the time direction and (MODE 1) the inverse of the operand scales
+                cp_async_wait<0>();
+                f2 dx2[kC / 2];
+                {
+                    const float4 b0 = raw[0], b1 = raw[kTile];
+                    if (cubic) {
+                        const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
+                        const f2 fr = pk(frac0, frac0);
+                        dx2[0] = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr));
+                        dx2[1] = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr));
+                        dx2[2] = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr));
+                        dx2[3] = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr));
+                    } else {
+                        dx2[0] = pk(b0.x, b0.y); dx2[1] = pk(b0.z, b0.w); dx2[2] = pk(b1.x, b1.y); dx2[3] = pk(b1.z, b1.w);
+                    }
+                    const float post = sign * inv_scale;          // +-1 in MODE 0; a power of two (exact) in MODE 1
+                    const f2 p2 = pk(post, post);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dx2[q] = mul2(dx2[q], p2);
+                }
+                if (more) fetch_row(idx1);
+                frac0 = frac1;
+                if (st + 2 < total) {                     // schedule entries are read a full stage ahead
+                    idx1 = a.stage_index[st + 2];
+                    frac1 = a.stage_frac[st + 2];
+                }
+
+                const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
+                if (tr) a.trace[st * 8 + 2] = clock64();
+                mbar_wait(&d_ready[t], phase);
+                phase ^= 1;
+                tc_fence_after();
+                if (tr) a.trace[st * 8 + 3] = clock64();
+
+                // ---- kv[h] = sum_c D[h*C + c] * dX[c]  (the bias is already in D); packed FFMA2, next TMEM
+                //      load in flight while the current 16 columns are consumed
+                float kv[kH];
+                {
+                    uint32_t va[16], vb[16];
+                    tmem_ld16_issue(taddr, va);
+#pragma unroll
+                    for (int j = 0; j < kN / 16; ++j) {
+                        uint32_t* cur = (j & 1) ? vb : va;
+                        tmem_ld16_wait(cur);
+                        if (j + 1 < kN / 16) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            f2 acc = mul2(pk(__uint_as_float(cur[8 * hh + 0]), __uint_as_float(cur[8 * hh + 1])), dx2[0]);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 2]), __uint_as_float(cur[8 * hh + 3])), dx2[1], acc);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 4]), __uint_as_float(cur[8 * hh + 5])), dx2[2], acc);
+                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 6]), __uint_as_float(cur[8 * hh + 7])), dx2[3], acc);
+                            float lo, hi;
+                            upk(acc, lo, hi);
+                            kv[2 * j + hh] = lo + hi;
+                        }
+                    }
+                }
+
+                if (tr) a.trace[st * 8 + 4] = clock64();
+                // ---- Runge-Kutta combination in registers, one rounding per operation in the order of
+                //      oracle/odeint_port.py, two hidden units per instruction; zn ends up in kv's registers
+                bool step_done = false;
+                const f2 dt2 = pk(dt, dt);
+                if (a.method == TCDE_RK4_38) {
+                    const f2 th2 = pk(third, third);
+                    if (sub == 0) {
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            k1[h] = kv[h]; k1[h + 1] = kv[h + 1];
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(dt2, pk(kv[h], kv[h + 1])), th2)), kv[h], kv[h + 1]);
+                        }
+                    } else if (sub == 1) {
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            s23[h] = kv[h]; s23[h + 1] = kv[h + 1];
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, sub2(pk(kv[h], kv[h + 1]), mul2(pk(k1[h], k1[h + 1]), th2)))),
+                                kv[h], kv[h + 1]);
+                        }
+                    } else if (sub == 2) {
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            const f2 k2p = pk(s23[h], s23[h + 1]), k3p = pk(kv[h], kv[h + 1]);
+                            upk(add2(pk(y[h], y[h + 1]), mul2(dt2, add2(sub2(pk(k1[h], k1[h + 1]), k2p), k3p))), kv[h], kv[h + 1]);
+                            upk(add2(k2p, k3p), s23[h], s23[h + 1]);
+                        }
+                    } else {
+                        const f2 three = pk(3.f, 3.f), eighth = pk(0.125f, 0.125f);
+#pragma unroll
+                        for (int h = 0; h < kH; h += 2) {
+                            const f2 sum = add2(add2(pk(k1[h], k1[h + 1]), mul2(three, pk(s23[h], s23[h + 1]))), pk(kv[h], kv[h + 1]));
+                            upk(add2(pk(y[h], y[h + 1]), mul2(mul2(sum, dt2), eighth)), kv[h], kv[h + 1]);
+                        }
+                        step_done = true;
+                    }
+                } else if (a.method == TCDE_MIDPOINT) {
+                    if (sub == 0) {
+                        const float half = E::mul(0.5f, dt);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) kv[h] = E::add(y[h], E::mul(kv[h], half));
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) kv[h] = E::add(y[h], E::mul(dt, kv[h]));
+                        step_done = true;
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) kv[h] = E::add(y[h], E::mul(dt, kv[h]));
+                    step_done = true;
+                }
+                if (tr) a.trace[st * 8 + 5] = clock64();
+                if (more) {                               // hand the next stage to the tensor core first ...
+                    write_a(kv, st + 1);
+                    if (issuer_warp) issue_stage(st + 1);
+                }
+                if (tr) a.trace[st * 8 + 6] = clock64();
+                if (step_done) {                          // ... then the bookkeeping that nobody waits for
+                    while (next_out == step) {
+                        const int mode = a.out_mode[jn];
+                        if (mode == 0) write_out(jn, y);
+                        else if (mode == 1) write_out(jn, kv);
+                        else {
+                            const float slope_w = a.out_slope[jn];
+                            float v[kH];
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) v[h] = E::add(y[h], E::mul(slope_w, E::sub(kv[h], y[h])));
+                            write_out(jn, v);
+                        }
+                        ++jn;
+                        next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+                    }
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) y[h] = kv[h];
+                    ++step;
+                    sub = 0;
+                    dt = dt_next;
+                    if (step + 1 < a.n_steps) dt_next = a.step_dt[step + 1];
+                } else {
+                    ++sub;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+
+template <int MODE> static int launch_tc(const UmmaArgs& a, cudaStream_t stream) {
+    const int64_t per_cta = tc::kTile * tc::kTiles;
+    const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
+    TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
+    auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, false, true>
+                             : a.trace ? tc::cdeint_tc_kernel<MODE, true, false> : tc::cdeint_tc_kernel<MODE, false, false>;
+    constexpr int smem = tc::Smem<MODE>::total + 1024;      // slack for the 1024-byte alignment of the tiles
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(unsigned)ctas, tc::kThreads, smem, stream>>>(a);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+int solve_tc_f32(const UmmaArgs& a, int H, int C, int mode, cudaStream_t stream) {
+    TCDE_CHECK_SUPPORTED(H == tc::kH && C == tc::kC, "tensor-core solve: built for hidden=32, channels=8 (got %d, %d)", H, C);
+    TCDE_CHECK_SUPPORTED((reinterpret_cast<uintptr_t>(a.control) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.z0) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+                         "tensor-core solve: control, z0 and out must be 16-byte aligned");
+    TCDE_CHECK_SUPPORTED(a.stage_dump == nullptr || (reinterpret_cast<uintptr_t>(a.stage_dump) & 15) == 0,
+                         "tensor-core solve: the stage dump must be 16-byte aligned");
+    return mode == 1 ? launch_tc<1>(a, stream) : launch_tc<0>(a, stream);
+}
+
+}  // namespace tcde
