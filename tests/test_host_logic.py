@@ -60,7 +60,7 @@ def test_spline_buffers_are_views_with_reference_names():
     assert X._b.data_ptr() == coeffs[..., 3:6].data_ptr()          # interpolation_cubic.py:297-305
     assert X.interval.tolist() == [0.0, 5.0] and X.grid_points.numel() == 6
     lin = cde.LinearInterpolation(torch.randn(2, 5, 3))
-    assert [n for n, _ in lin.named_buffers()] == ["_t", "_coeffs"]
+    assert [n for n, _ in lin.named_buffers()] == ["_t", "_coeffs", "_derivs"]     # interpolation_linear.py:191-193
 
 
 @pytest.mark.parametrize("dtype_t", [torch.float32, torch.float64])

@@ -10,7 +10,7 @@ import warnings
 
 import torch
 
-from . import _lib
+from . import _diff, _lib
 
 
 # --------------------------------------------------------------------------- validation
@@ -45,11 +45,13 @@ def validate_input_path(x, t):
     return t
 
 
-def _no_autograd(name, *tensors):
-    if torch.is_grad_enabled() and any(x is not None and x.requires_grad for x in tensors):
-        raise NotImplementedError(
-            "torchcde_b200.{}: differentiating through the coefficient builders is not implemented; build the "
-            "coefficients under torch.no_grad() (they are preprocessing, interpolation_cubic.py:216-226).".format(name))
+def _differentiable(kernel, formula, x, t):
+    """The builders are differentiable in the data and in the knots like the reference's (test_tricks.py:21-49):
+    ``kernel`` always produces the values; when ``x`` or ``t`` require grad the result carries a backward pass that
+    recomputes ``formula`` (torchcde_b200/_diff.py) with torch operators.  ``t`` may be None."""
+    if t is None:
+        return _diff.with_kernel_forward(lambda xx: kernel(xx, None), lambda xx: formula(xx, None), x)
+    return _diff.with_kernel_forward(kernel, formula, x, t)
 
 
 def _paths(x):
@@ -96,17 +98,20 @@ def forward_fill(x, fill_index=-2):
     assert x.dim() >= 2
     _lib.require_cuda(x)
     _lib.dtype_code(x.dtype)
-    _no_autograd("forward_fill", x)
     moved = x.movedim(fill_index, -2) if fill_index not in (-2, x.dim() - 2) else x
-    with torch.cuda.device(x.device):
-        flat, batch = _paths(moved)
-        out = torch.empty_like(flat)
-        flags = _flags(flat)
-        p, length, channels = flat.shape
-        if flat.numel() > 0:
-            _lib.call("tcde_forward_fill", _lib.ptr(flat), _lib.ptr(out), p, length, channels,
-                      _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
-    out = out.view(*batch, length, channels)
+
+    def kernel(src):
+        with torch.cuda.device(src.device):
+            flat, batch = _paths(src)
+            out = torch.empty_like(flat)
+            flags = _flags(flat)
+            p, length, channels = flat.shape
+            if flat.numel() > 0:
+                _lib.call("tcde_forward_fill", _lib.ptr(flat), _lib.ptr(out), p, length, channels,
+                          _lib.dtype_code(flat.dtype), _lib.ptr(flags), _lib.stream_of(flat))
+        return out.view(*batch, length, channels)
+
+    out = _diff.with_kernel_forward(kernel, _diff.forward_fill, moved)
     return out.movedim(-2, fill_index) if moved is not x else out
 
 
@@ -130,16 +135,8 @@ def _prepare_rectilinear_interpolation(data, time_index):
     return out.view(*batch, 2 * length - 1, channels), bool(seen & _lib.FLAG_NAN_FIRST_ROW)
 
 
-def linear_interpolation_coeffs(x, t=None, rectilinear=None):
-    """interpolation_linear.py:131-171.  Without NaNs (and without ``rectilinear``) the input
-    tensor itself is returned, like the reference (:169-171)."""
-    if not x.is_floating_point():
-        raise ValueError("X must both be floating point.")
-    if rectilinear is None:
-        validate_input_path(x, t)
-    _lib.require_cuda(x, t)
-    _lib.dtype_code(x.dtype)
-    _no_autograd("linear_interpolation_coeffs", x, t)
+def _linear_kernel(x, t, rectilinear):
+    """The kernel path of ``linear_interpolation_coeffs``: returns ``x`` itself when nothing had to be done."""
     with torch.cuda.device(x.device):
         if rectilinear is not None:
             if x.ndimension() < 2:
@@ -153,33 +150,50 @@ def linear_interpolation_coeffs(x, t=None, rectilinear=None):
                               "of each channel with whatever you'd like it to be. (The mean over that channel is a "
                               "common choice.)")
             t_full = validate_input_path(x, t)
-            has_nan = starts_with_nan
-        else:
-            # one pass: the fill kernel also reports whether there was anything to fill (linear.py:169-171)
-            t_full = validate_input_path(x, t)
+            if not starts_with_nan:
+                return x
             flat, batch = _paths(x)
-            if flat.numel() == 0:
-                return x
             knots = None if t is None else _knots_arg(t_full, x)
-            flags = _flags(flat)
-            out = _fill(flat, knots, flags)
-            if not flags.item() & _lib.FLAG_NAN_SEEN:
-                return x
+            out = _fill(flat, knots)
             return out.view(*batch, x.size(-2), x.size(-1))
-        if not has_nan:
-            return x
+        # one pass: the fill kernel also reports whether there was anything to fill (linear.py:169-171)
+        t_full = validate_input_path(x, t)
         flat, batch = _paths(x)
+        if flat.numel() == 0:
+            return x
         knots = None if t is None else _knots_arg(t_full, x)
-        out = _fill(flat, knots)
+        flags = _flags(flat)
+        out = _fill(flat, knots, flags)
+        if not flags.item() & _lib.FLAG_NAN_SEEN:
+            return x
         return out.view(*batch, x.size(-2), x.size(-1))
 
 
-# --------------------------------------------------------------------------- Hermite
-def hermite_cubic_coefficients_with_backward_differences(x, t=None):
-    """interpolation_hermite_cubic_bdiff.py:23-44: (..., L, C) -> (..., L-1, 4C)."""
-    t_full = validate_input_path(x, t)
+def linear_interpolation_coeffs(x, t=None, rectilinear=None):
+    """interpolation_linear.py:131-171.  Without NaNs (and without ``rectilinear``) the input
+    tensor itself is returned, like the reference (:169-171)."""
+    if not x.is_floating_point():
+        raise ValueError("X must both be floating point.")
+    if rectilinear is None:
+        validate_input_path(x, t)
     _lib.require_cuda(x, t)
-    _no_autograd("hermite_cubic_coefficients_with_backward_differences", x, t)
+    _lib.dtype_code(x.dtype)
+    with torch.no_grad():
+        out = _linear_kernel(x.detach(), None if t is None else t.detach(), rectilinear)
+    if rectilinear is None and out.data_ptr() == x.data_ptr() and out.shape == x.shape:
+        return x                                   # nothing was missing: the input itself (and its autograd history)
+
+    def formula(xx, tt):
+        if rectilinear is not None:
+            xx = _diff.rectilinear(xx, rectilinear)
+        return _diff.linear_fill(xx, tt)
+
+    return _differentiable(lambda *_: out, formula, x, t)
+
+
+# --------------------------------------------------------------------------- Hermite
+def _hermite_kernel(x, t):
+    t_full = validate_input_path(x, t)
     with torch.cuda.device(x.device):
         flat, batch = _paths(x)
         p, length, channels = flat.shape
@@ -200,11 +214,23 @@ def hermite_cubic_coefficients_with_backward_differences(x, t=None):
     return out.view(*batch, length - 1, 4 * channels)
 
 
+def hermite_cubic_coefficients_with_backward_differences(x, t=None):
+    """interpolation_hermite_cubic_bdiff.py:23-44: (..., L, C) -> (..., L-1, 4C)."""
+    validate_input_path(x, t)
+    _lib.require_cuda(x, t)
+    return _differentiable(_hermite_kernel, _diff.hermite, x, t)
+
+
 # --------------------------------------------------------------------------- natural cubic
 def _natural(x, t, version, name):
-    t_full = validate_input_path(x, t)
+    validate_input_path(x, t)
     _lib.require_cuda(x, t)
-    _no_autograd(name, x, t)
+    return _differentiable(lambda xx, tt: _natural_kernel(xx, tt, version), lambda xx, tt: _diff.natural(xx, tt, version),
+                           x, t)
+
+
+def _natural_kernel(x, t, version):
+    t_full = validate_input_path(x, t)
     with torch.cuda.device(x.device):
         flat, batch = _paths(x)
         p, length, channels = flat.shape

@@ -6,13 +6,14 @@ reference (interpolation_base.py:5-22, interpolation_cubic.py:268-346,
 interpolation_linear.py:174-225).  The buffers are *views* of the coefficient tensor, as in
 the reference (:297-305).  Evaluation at a tensor of times runs ``tcde_spline_eval`` (one
 launch, no host sync); the interval index of every query time is computed with the
-reference's own ``bucketize`` arithmetic so it is bit-exact.
+reference's own ``bucketize`` arithmetic so it is bit-exact.  ``evaluate`` / ``derivative`` are
+differentiable in the coefficients, the knots and the query times (backward pass: ``_diff.py``).
 """
 import abc
 
 import torch
 
-from . import _lib
+from . import _diff, _lib
 from .schedule import locate
 
 
@@ -115,10 +116,19 @@ class CubicSpline(InterpolationBase):
         return locate(self._t, t, maxlen + 1)
 
     def _eval(self, t, derivative):
+        t = torch.as_tensor(t, dtype=self._b.dtype, device=self._b.device)
         fractional_part, index = self._interpret_t(t)
-        knots = self._t.detach().to(self._b.dtype).contiguous()
-        return _eval_kernel(self._rows().detach(), knots, self._b.size(-2), self.channels, index,
-                            fractional_part.detach(), _lib.CONTROL_CUBIC, derivative)
+
+        def kernel(*_):
+            knots = self._t.detach().to(self._b.dtype).contiguous()
+            return _eval_kernel(self._rows().detach(), knots, self._b.size(-2), self.channels, index,
+                                fractional_part.detach(), _lib.CONTROL_CUBIC, derivative)
+
+        # differentiable in the coefficients, the knots and the query times like the reference's torch operators
+        # (interpolation_cubic.py:315-336): the backward pass recomputes the polynomial with torch operators
+        return _diff.with_kernel_forward(
+            kernel, lambda a, b, c, d, k, tt: _diff.cubic_eval(a, b, c, d, k.to(tt.dtype), tt, index, derivative),
+            self._a, self._b, self._two_c, self._three_d, self._t, t)
 
     def evaluate(self, t):
         return self._eval(t, False)
@@ -145,15 +155,20 @@ class LinearInterpolation(InterpolationBase):
         # state_dict keys ``_t``, ``_coeffs``, ``_derivs``); on the GPU they come from the evaluation kernel (the same
         # ``(x[i+1] - x[i]) / (t[i+1] - t[i])``, bit-identical); a module built from CPU tensors (to be moved with
         # ``.to(device)`` before use) forms them with the reference's own two torch ops
+        def slopes(c, k):
+            return (c[..., 1:, :] - c[..., :-1, :]) / (k[1:] - k[:-1]).unsqueeze(-1)
+
         if coeffs.is_cuda:
-            n = coeffs.size(-2) - 1
-            index = torch.arange(n, device=coeffs.device)
-            frac = torch.zeros(n, dtype=coeffs.dtype, device=coeffs.device)
-            knots = t.detach().to(device=coeffs.device, dtype=coeffs.dtype).contiguous()
-            derivs = _eval_kernel(coeffs.detach(), knots, coeffs.size(-2), coeffs.size(-1), index, frac,
-                                  _lib.CONTROL_LINEAR, True)
+            def kernel(c, k):
+                n = c.size(-2) - 1
+                index = torch.arange(n, device=c.device)
+                frac = torch.zeros(n, dtype=c.dtype, device=c.device)
+                knots = k.to(device=c.device, dtype=c.dtype).contiguous()
+                return _eval_kernel(c, knots, c.size(-2), c.size(-1), index, frac, _lib.CONTROL_LINEAR, True)
+
+            derivs = _diff.with_kernel_forward(kernel, slopes, coeffs, t)
         else:
-            derivs = (coeffs[..., 1:, :] - coeffs[..., :-1, :]) / (t[1:] - t[:-1]).unsqueeze(-1)
+            derivs = slopes(coeffs, t)
 
         self.register_buffer('_t', t)
         self.register_buffer('_coeffs', coeffs)
@@ -177,10 +192,16 @@ class LinearInterpolation(InterpolationBase):
         return locate(self._t, t, maxlen + 1)
 
     def _eval(self, t, derivative):
+        t = torch.as_tensor(t, dtype=self._coeffs.dtype, device=self._coeffs.device)
         fractional_part, index = self._interpret_t(t)
-        knots = self._t.detach().to(self._coeffs.dtype).contiguous()
-        return _eval_kernel(self._coeffs.detach(), knots, self._coeffs.size(-2), self.channels, index,
-                            fractional_part.detach(), _lib.CONTROL_LINEAR, derivative)
+
+        def kernel(*_):
+            knots = self._t.detach().to(self._coeffs.dtype).contiguous()
+            return _eval_kernel(self._coeffs.detach(), knots, self._coeffs.size(-2), self.channels, index,
+                                fractional_part.detach(), _lib.CONTROL_LINEAR, derivative)
+
+        return _diff.with_kernel_forward(
+            kernel, lambda c, k, tt: _diff.linear_eval(c, k.to(tt.dtype), tt, index, derivative), self._coeffs, self._t, t)
 
     def evaluate(self, t):
         return self._eval(t, False)
