@@ -161,7 +161,9 @@ class Dopri5:
         # the last beta row equals the solution weights (FSAL): y1 is the 5th-order solution
         return y1, ks, _error_ratio(y0, y1, ks, _C_ERROR, dt, self.atol, self.rtol, self.norm)
 
-    def integrate(self, times):
+    def integrate(self, times, targets=None):
+        """``targets``: optional 1-D tensor holding the same output times; when given, the dense output is evaluated at
+        the tensor entries so that autograd sees the dependence on the requested times (adjoint=False)."""
         out = [self.y0]
         t0 = times[0]
         y0 = self.y0
@@ -171,7 +173,7 @@ class Dopri5:
         t_lo, t_hi = t0, t0
         coeff = None
         jumps = [v for v in self.jump_t if v > t0]
-        for target in times[1:]:
+        for n_target, target in enumerate(times[1:], 1):
             tries = 0
             while target > t_hi:
                 if tries >= self.max_num_steps:
@@ -196,7 +198,7 @@ class Dopri5:
                     self.n_rejected += 1
                 dt = _next_step(step, ratio)
                 tries += 1
-            out.append(self._evaluate(coeff, t_lo, t_hi, target))
+            out.append(self._evaluate(coeff, t_lo, t_hi, target if targets is None else targets[n_target]))
         return torch.stack(out, dim=0)
 
     @staticmethod
@@ -217,7 +219,7 @@ class Dopri5:
         return total
 
 
-def odeint_dopri5(field, y0, times, rtol, atol, options=None):
+def odeint_dopri5(field, y0, times, rtol, atol, options=None, targets=None):
     """``times``: increasing Python floats.  Returns (len(times), *y0.shape)."""
     options = dict(options or {})
     jump_t = options.pop("jump_t", None)
@@ -227,7 +229,7 @@ def odeint_dopri5(field, y0, times, rtol, atol, options=None):
                     max_num_steps=options.pop("max_num_steps", 2 ** 31 - 1), jump_t=jump_t)
     if options:
         raise NotImplementedError("dopri5: unsupported options {}".format(sorted(options)))
-    out = solver.integrate(list(times))
+    out = solver.integrate(list(times), targets)
     return out, solver
 
 
@@ -274,8 +276,11 @@ class _Adjoint(torch.autograd.Function):
     with the same solver family, evaluating the vector field under autograd for its VJPs."""
 
     @staticmethod
-    def forward(ctx, forward_solve, vf, times, solve_aug, fused_vjp, fixed_spec, y0, *params):
+    def forward(ctx, forward_solve, vf, times, solve_aug, fused_vjp, fixed_spec, flipped, t_tensor, y0, *params):
         ctx.vf, ctx.times, ctx.solve_aug, ctx.fused_vjp, ctx.fixed_spec = vf, times, solve_aug, fused_vjp, fixed_spec
+        ctx.flipped = flipped
+        ctx.t_needs_grad = t_tensor is not None and t_tensor.requires_grad
+        ctx.t_meta = None if t_tensor is None else (t_tensor.dtype, t_tensor.device)
         with torch.no_grad():
             ys = forward_solve(y0)
         ctx.save_for_backward(ys, *params)
@@ -286,10 +291,12 @@ class _Adjoint(torch.autograd.Function):
         ys, *params = ctx.saved_tensors
         vf, times = ctx.vf, ctx.times
         params = tuple(params)
-        if ctx.fused_vjp is not None and ctx.fixed_spec is not None:
+        if ctx.fused_vjp is not None and ctx.fixed_spec is not None and not ctx.t_needs_grad:
             with torch.no_grad():
                 a_y, a_p = _fused_fixed_backward(ctx.fused_vjp, times, ys, grad_ys, *ctx.fixed_spec)
-            return (None, None, None, None, None, None, a_y, *a_p)
+            return (None, None, None, None, None, None, None, None, a_y, *a_p)
+        if ctx.t_needs_grad:
+            return _Adjoint._backward_with_times(ctx, ys, params, grad_ys)
         shapes = [ys[0].shape, ys[0].shape] + [p.shape for p in params]
         sizes = [s.numel() for s in shapes]
 
@@ -326,7 +333,59 @@ class _Adjoint(torch.autograd.Function):
                 flat1 = ctx.solve_aug(lambda s, v: -aug_field(-s, v), flat0, [-times[i], -times[i - 1]])[-1]
                 _, a_y, *a_p = [x.clone() for x in unpack(flat1)]
                 a_y = a_y + grad_ys[i - 1]
-        return (None, None, None, None, None, None, a_y, *a_p)
+        return (None, None, None, None, None, None, None, None, a_y, *a_p)
+
+    @staticmethod
+    def _backward_with_times(ctx, ys, params, grad_ys):
+        """The same backward solve with torchdiffeq's time gradients: the augmented state carries one more scalar,
+        the integral of -a^T df/dt, and every output time t_i gets dL/dt_i = <f(t_i, y_i), dL/dy_i> (``odeint_adjoint``
+        with ``t.requires_grad``).  Autograd serves the field (its time dependence is the control's dX/dt)."""
+        vf, times = ctx.vf, ctx.times
+        shapes = [torch.Size([]), ys[0].shape, ys[0].shape] + [p.shape for p in params]
+        sizes = [max(1, s.numel()) for s in shapes]
+
+        def pack(parts):
+            return torch.cat([p.reshape(-1) for p in parts])
+
+        def unpack(flat):
+            outs, off = [], 0
+            for shape, n in zip(shapes, sizes):
+                outs.append(flat[off:off + n].view(shape))
+                off += n
+            return outs
+
+        def aug_field(t, flat):
+            _, y, a_y, *_ = unpack(flat)
+            with torch.enable_grad():
+                t_ = torch.tensor(t, dtype=torch.float64, device=ys.device, requires_grad=True)
+                y_ = y.detach().requires_grad_(True)
+                f = vf(t_, y_)
+                grads = torch.autograd.grad(f, (t_, y_) + params, -a_y, allow_unused=True)
+            vjp_t = grads[0].to(ys.dtype) if grads[0] is not None else torch.zeros((), dtype=ys.dtype, device=ys.device)
+            vjp_y = grads[1] if grads[1] is not None else torch.zeros_like(y)
+            vjp_p = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads[2:], params)]
+            return pack([vjp_t, f.detach(), vjp_y] + vjp_p)
+
+        with torch.no_grad():
+            time_vjps = [None] * len(times)
+            a_t = torch.zeros((), dtype=ys.dtype, device=ys.device)
+            a_y = grad_ys[-1].clone()
+            a_p = [torch.zeros_like(p) for p in params]
+            for i in range(len(times) - 1, 0, -1):
+                f_i = vf(times[i], ys[i])
+                d_cur = (f_i.reshape(-1) * grad_ys[i].reshape(-1)).sum()
+                a_t = a_t - d_cur
+                time_vjps[i] = d_cur
+                flat0 = pack([a_t, ys[i], a_y] + a_p)
+                flat1 = ctx.solve_aug(lambda s, v: -aug_field(-s, v), flat0, [-times[i], -times[i - 1]])[-1]
+                a_t, _, a_y, *a_p = [x.clone() for x in unpack(flat1)]
+                a_y = a_y + grad_ys[i - 1]
+            time_vjps[0] = a_t
+            grad_t = torch.stack(time_vjps)
+            if ctx.flipped:                # the solve ran in s = -t
+                grad_t = -grad_t
+            grad_t = grad_t.to(dtype=ctx.t_meta[0], device=ctx.t_meta[1])
+        return (None, None, None, None, None, None, None, grad_t, a_y, *a_p)
 
 
 def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
@@ -405,11 +464,12 @@ def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):
     return a_y, grads
 
 
-def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params, fused_vjp=None, fixed_spec=None):
+def solve_with_adjoint(forward_solve, vf, times, solve_aug, y0, params, fused_vjp=None, fixed_spec=None, t_tensor=None,
+                       flipped=False):
     """``forward_solve(y0) -> ys`` (time first); ``vf(t_float, y)`` differentiable in y and ``params``.
 
     ``fused_vjp(params)``, if given, returns ``None`` or a callable ``(t, y, a, scale) -> (f, scale * a^T df/dy,
     [scale * a^T df/dp for p in params])`` that replaces autograd in the backward solve."""
-    params = tuple(p for p in params if p.requires_grad)
+    params = tuple(p for p in params if p.requires_grad and p is not t_tensor)
     stage = fused_vjp(params) if fused_vjp is not None else None
-    return _Adjoint.apply(forward_solve, vf, times, solve_aug, stage, fixed_spec, y0, *params)
+    return _Adjoint.apply(forward_solve, vf, times, solve_aug, stage, fixed_spec, flipped, t_tensor, y0, *params)

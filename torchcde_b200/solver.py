@@ -223,6 +223,7 @@ def _generic_solve(X, func, z0, t, method, step_size, is_prod, known_control):
     sync inside the time loop for the built-in controls."""
     n_rows = _control_signature(X)[3] if known_control else None
     dtype = z0.dtype
+    third, two_thirds_ = 1 / 3, 2 / 3
     if known_control:
         sched = build_schedule(t, _schedule_knots(X), n_rows, method, step_size, dtype)
         idx = sched.stage_index.tolist()
@@ -233,6 +234,32 @@ def _generic_solve(X, func, z0, t, method, step_size, is_prod, known_control):
     dts = sched.step_dt.to(z0.device)
     slopes = sched.out_slope.to(z0.device)
     sign = sched.sign
+    if torch.is_grad_enabled() and (t.requires_grad or (known_control and X._t.requires_grad)):
+        # gradients with respect to the output times / the knots (test_tricks.py:21-49): the same grid, stage times,
+        # fractions and output weights as the host schedule, but as torch expressions of ``t`` and ``X._t`` on the
+        # device (torchdiffeq builds its grid from the ``t`` tensor too, so autograd sees the same dependence)
+        tt = (t if sign > 0 else -t).to(z0.device)
+        n_grid = sched.grid.numel()
+        if step_size is None:
+            grid_t = tt
+        else:
+            inner = tt[0] + torch.arange(n_grid - 1, dtype=tt.dtype, device=tt.device) * step_size
+            grid_t = torch.cat([inner, tt[-1:]])
+        g0, g1 = grid_t[:-1], grid_t[1:]
+        gdt = g1 - g0
+        if method == "rk4":
+            st = torch.stack([g0, g0 + gdt * third, g0 + gdt * two_thirds_, g1], dim=1)
+        elif method == "midpoint":
+            st = torch.stack([g0, g0 + 0.5 * gdt], dim=1)
+        else:
+            st = g0.unsqueeze(1)
+        times_dev = (st if sign > 0 else -st).to(dtype)
+        dts = gdt.to(dtype)
+        if known_control:
+            index_dev = sched.stage_index.to(z0.device).long()
+            frac_dev = times_dev.to(X._t.dtype) - X._t[index_dev]
+        steps = sched.out_step.clamp(min=0).to(z0.device).long()
+        slopes = ((tt - g0[steps]) / (g1[steps] - g0[steps])).to(dtype)
 
     def field(i, s, z):
         ts = times_dev[i, s]
@@ -449,16 +476,23 @@ def _kernel_vjp(X, weight, bias, z0, params):
 
 
 def _torch_field(X, func, is_prod, known_control, z0):
-    """The reference's ``_VectorField.forward`` (solver.py:117-135) as differentiable torch ops."""
+    """The reference's ``_VectorField.forward`` (solver.py:117-135) as differentiable torch ops.  ``t`` is a Python
+    float, or a 0-dim tensor when the gradient with respect to time is wanted (the adjoint's time vjps)."""
     where = _host_locator(X, z0.dtype) if known_control else None
 
     def field(t, y, nudge=0):
-        ts = torch.tensor(t, dtype=torch.float64).to(z0.dtype)
+        if isinstance(t, torch.Tensor):
+            tf = float(t.detach())
+            ts = t.to(device=y.device, dtype=z0.dtype)
+        else:
+            tf = t
+            ts = torch.tensor(t, dtype=torch.float64).to(z0.dtype).to(y.device)
         if nudge:
             ts = torch.nextafter(ts, ts + 1)
-        ts = ts.to(y.device)
         if known_control:
-            index, frac = where(t, nudge)
+            index, frac = where(tf, nudge)
+            if torch.is_grad_enabled() and (ts.requires_grad or X._t.requires_grad):
+                frac = ts.to(X._t.dtype) - X._t[index]          # differentiable in the time and in the knots
             dx = _derivative_at(X, index, frac)
         else:
             dx = X.derivative(ts)
@@ -635,18 +669,25 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                 return adaptive.odeint_fixed(f, v, ts, a_method, a_options.get("step_size", None))
             return adaptive.odeint_dopri5(f, v, ts, a_rtol, a_atol)[0]
 
+        t_grad = t if t.requires_grad else None
+
         def fused_vjp(params):
-            if field_params is None or flipped:          # decreasing t: autograd (rare; keeps one code path)
+            # decreasing t, gradients with respect to the output times, or parameters that are not the linear map
+            # (the control's coefficients or knots in ``adjoint_params``): autograd serves the backward solve
+            if field_params is None or flipped or t_grad is not None:
                 return None
             return _kernel_vjp(X, field_params[0], field_params[1], z0, params)
 
         fixed_spec = (a_method, a_options.get("step_size", None)) if a_method in FIXED_METHODS else None
         ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params,
-                                         fused_vjp, fixed_spec)
+                                         fused_vjp, fixed_spec, t_grad, flipped)
         return _time_first_to_reference_layout(ys)
 
     # adjoint=False: backpropagate through the solver's own operations, like torchdiffeq.odeint
     if method in FIXED_METHODS:
         return _generic_solve(X, func, z0, t, method, step_size, is_prod, sig is not None)
-    ys = adaptive.odeint_dopri5(autograd_field(), z0, times, rtol, atol, options)[0]
+    targets = None
+    if t.requires_grad:
+        targets = (-t if flipped else t).to(z0.device)
+    ys = adaptive.odeint_dopri5(autograd_field(), z0, times, rtol, atol, options, targets)[0]
     return _time_first_to_reference_layout(ys)
