@@ -210,6 +210,25 @@ TCDE_API int64_t tcde_error_ratio_partials(int64_t n);
 TCDE_API int tcde_error_ratio_sumsq(const void* y0, const void* y1, const void* const* terms, const double* coefs,
                            int n_terms, double atol, double rtol, int64_t n, int dtype, void* partials, void* stream);
 
+/* Device-controlled Dormand-Prince 5(4) for the linear vector field (float32, hidden = 32, channels = 8) -- replaces what
+ * the reference obtains from torchdiffeq's adaptive solver behind torchcde/solver.py:226-227 (default method of cdeint).
+ * ONE launch = one attempted step of the whole batch; accept / reject, the step-size rule and the dense output at the
+ * requested times run on the device, so the host only reads the control block once per chunk of launches.
+ *   state     float  [5][n_paths][32]: Y0, Y1, F0, F1, MID.  Before the first launch Y0 = y(t0), F0 = f(t0, y(t0)).
+ *   partials  double [2][tcde_dopri5_linear_grid(n_paths)]
+ *   ctl       double [2][16]: slot 1 is read by launch 0.  Fields: 0 t, 1 dt, 2 t_end, 3 rtol, 4 atol, 5 current state
+ *             buffer, 6 done, 7 pending (an undecided attempt exists), 8 accepted, 9 rejected, 10 next output index (>= 1),
+ *             11 number of partials, 12 need_mid, 13 last error ratio, 14 launches.  Launch seq reads slot (seq + 1) & 1
+ *             and writes slot seq & 1.
+ *   out       float  [n_paths][n_out][32]; the caller writes out[:, 0] = y(t0).  out_times: device double [n_out], increasing
+ *             (negated for a decreasing t, sign = -1).
+ * Enqueues launches first_seq .. first_seq + n_launches - 1 on the stream; launches after the end are no-ops. */
+TCDE_API int tcde_dopri5_linear_grid(int64_t n_paths);
+TCDE_API int tcde_dopri5_linear_attempts(const void* control, int control_kind, int64_t n_rows, const void* knots,
+                                const void* weight, const void* bias, void* state, void* partials, void* ctl, void* out,
+                                const void* out_times, int64_t n_out, int64_t n_paths, int64_t channels, int64_t hidden,
+                                double sign, int64_t first_seq, int64_t n_launches, int dtype, void* stream);
+
 /* Profiling aid: a device buffer of 64 x 8 int64 that the tensor-core solve kernel (variant 2)
  * fills with clock64 stamps of CTA 0 / tile 0 for its first 64 stages; NULL (default) disables. */
 TCDE_API int tcde_set_trace_buffer(void* device_buffer);
@@ -221,8 +240,9 @@ TCDE_API int tcde_set_natural_variant(int variant);
 
 /* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic (the tcgen05 kernel
  * where it is built for the shape: hidden = 32, channels = 8; the CUDA-core kernel otherwise),
- * 1 = CUDA-core kernel, 2 = tcgen05 kernel (TCDE_ERR_UNSUPPORTED for other shapes).
- * Process-wide; meant for tests and benchmarks. */
+ * 1 = CUDA-core kernel, 2 = round-1 tcgen05 kernel (3xTF32, Runge-Kutta slopes parked in shared memory), 3 / 4 = round-2
+ * tcgen05 kernel (solve_tc.cu: slopes in registers) with the 3xTF32 / the 2xFP16 operand split (TCDE_ERR_UNSUPPORTED
+ * for other shapes).  Process-wide; meant for tests and benchmarks. */
 TCDE_API int tcde_set_solve_variant(int variant);
 
 #ifdef __cplusplus

@@ -51,7 +51,7 @@ _ORDER = 5
 
 
 def _rms(x):
-    return float(x.pow(2).mean().sqrt())
+    return float(x.detach().pow(2).mean().sqrt())
 
 
 def _kernels_apply(*tensors):
@@ -319,7 +319,9 @@ class _Adjoint(torch.autograd.Function):
             with torch.enable_grad():
                 y_ = y.detach().requires_grad_(True)
                 f = vf(t, y_)
-                grads = torch.autograd.grad(f, (y_,) + params, -a_y, allow_unused=True)
+                # retain_graph: the part of the graph that is shared between calls (views of a coefficient tensor that is
+                # itself an adjoint parameter) must survive, like in torchdiffeq's augmented dynamics
+                grads = torch.autograd.grad(f, (y_,) + params, -a_y, allow_unused=True, retain_graph=True)
             vjp_y = grads[0] if grads[0] is not None else torch.zeros_like(y)
             vjp_p = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads[1:], params)]
             return pack([f.detach(), vjp_y] + vjp_p)
@@ -360,7 +362,7 @@ class _Adjoint(torch.autograd.Function):
                 t_ = torch.tensor(t, dtype=torch.float64, device=ys.device, requires_grad=True)
                 y_ = y.detach().requires_grad_(True)
                 f = vf(t_, y_)
-                grads = torch.autograd.grad(f, (t_, y_) + params, -a_y, allow_unused=True)
+                grads = torch.autograd.grad(f, (t_, y_) + params, -a_y, allow_unused=True, retain_graph=True)
             vjp_t = grads[0].to(ys.dtype) if grads[0] is not None else torch.zeros((), dtype=ys.dtype, device=ys.device)
             vjp_y = grads[1] if grads[1] is not None else torch.zeros_like(y)
             vjp_p = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads[2:], params)]

@@ -19,9 +19,7 @@
 //
 // CTA anatomy: two tiles of 128 paths, thread = path (256 threads); accumulators [128 x 256] fp32 per tile in TMEM (all
 // 512 columns); a_ready[t] (128 arrivals) / d_ready[t] (tcgen05.commit) mbarriers.
-#include <cuda_fp16.h>
-
-#include "umma.cuh"
+#include "tc_common.cuh"
 
 namespace tcde {
 
@@ -35,27 +33,6 @@ constexpr int kN = kH * kC;       // 256 accumulator columns per tile
 constexpr int kTile = 128;
 constexpr int kTiles = 2;
 constexpr int kThreads = kTile * kTiles;
-
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {          // (lo, hi) -> f16x2, round to nearest even
-    uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ void unpack_h2(uint32_t h, float& lo, float& hi) {
-    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
-}
-__device__ __forceinline__ int exponent_of(float m) { return (int)((__float_as_uint(m) >> 23) & 0xFFu); }   // biased
-__device__ __forceinline__ float pow2_biased(int e) { return __uint_as_float((uint32_t)e << 23); }          // 2^(e-127)
 
 // shared-memory map (bytes).  MODE 0: TF32 hi / lo tiles (K = 32 floats = one 128-byte row each);
 // MODE 1: one FP16 tile per operand, row = [hi(32) | lo(32)] halves = 128 bytes.
@@ -71,10 +48,6 @@ template <int MODE> struct Smem {
     static constexpr int bars = red + 256;
     static constexpr int total = bars + 64;
 };
-
-// byte offset of (row, 16-byte chunk) in a K-major no-swizzle tile of 32-byte rows: 8-row groups 256 B apart (SBO),
-// the two K chunks 128 B apart (LBO), rows 16 B apart
-__device__ __forceinline__ uint32_t aug_off(int row, int chunk) { return (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16); }
 
 template <int MODE, bool TRACE, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a) {
