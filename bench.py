@@ -97,6 +97,23 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_ready(self, timeout=20.0):
+        """Block until nvidia-smi has written its first sample (its start-up on a fresh box can take seconds, longer
+        than the whole timed region -- BENCH_r01 had 'no samples' for that reason)."""
+        if self.proc is None:
+            return False
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            try:
+                if os.path.getsize(self.file.name) > 0:
+                    return True
+            except OSError:
+                pass
+            if self.proc.poll() is not None:
+                return False
+            time.sleep(0.05)
+        return False
+
     def mark(self, t_begin, t_end):
         self.window = (t_begin, t_end)
 
@@ -321,6 +338,8 @@ def run_gpu_arm(args):
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize(device)
+        if rank == 0:
+            sampler.wait_ready()
         wall_begin = time.time()
         ms = time_loop(step, args.steps, 0, device, dist)
         wall_end = time.time()

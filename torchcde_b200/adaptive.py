@@ -24,6 +24,7 @@ per evaluation (``tcde_vector_field_linear_vjp``); the stage combinations and th
 attempt are single launches too (``tcde_linear_combination`` / ``tcde_error_ratio_sumsq``).
 """
 import ctypes
+import math
 
 import torch
 
@@ -231,6 +232,60 @@ def odeint_dopri5(field, y0, times, rtol, atol, options=None, targets=None):
         raise NotImplementedError("dopri5: unsupported options {}".format(sorted(options)))
     out = solver.integrate(list(times), targets)
     return out, solver
+
+
+# ----------------------------------------------------- dopri5 with the controller on the device (linear field)
+_DEVICE_CHUNK = 48          # launches enqueued between two reads of the done flag
+
+
+def device_dopri5_available(z0, channels):
+    return (z0.is_cuda and z0.dtype == torch.float32 and z0.size(-1) == 32 and channels == 8 and z0.numel() > 0)
+
+
+def odeint_dopri5_device(control, kind, n_rows, knots, weight, bias, field, y0, times, rtol, atol, sign, first_step=None):
+    """The same algorithm as ``Dopri5.integrate`` with accept / reject, the step-size rule and the dense output on the
+    device (``tcde_dopri5_linear_attempts``: one launch per attempted step, no host read per attempt).  ``field`` is only
+    used for the slope at the start and Hairer's initial step.  ``times``: increasing floats (already negated when
+    ``sign`` < 0).  Returns ``(out (len(times), *y0.shape), stats)``."""
+    lib = _lib.load()
+    shape = y0.shape
+    hidden = shape[-1]
+    yf = y0.detach().reshape(-1, hidden).contiguous()
+    n_paths = yf.size(0)
+    dev = yf.device
+    t0 = times[0]
+    with torch.no_grad():
+        f0 = field(t0, yf)
+        dt = first_step if first_step is not None else _initial_step(field, t0, yf, f0, rtol, atol)
+        state = torch.empty(5, n_paths, hidden, dtype=torch.float32, device=dev)
+        state[0].copy_(yf)
+        state[2].copy_(f0)
+        grid = lib.tcde_dopri5_linear_grid(n_paths)
+        partials = torch.zeros(2, grid, dtype=torch.float64, device=dev)
+        ctl_host = torch.zeros(2, 16, dtype=torch.float64)
+        ctl_host[1, 0], ctl_host[1, 1], ctl_host[1, 2] = t0, dt, times[-1]
+        ctl_host[1, 3], ctl_host[1, 4] = rtol, atol
+        ctl_host[1, 10] = 1                       # next output index
+        ctl = ctl_host.to(dev)
+        out = torch.empty(n_paths, len(times), hidden, dtype=torch.float32, device=dev)
+        out[:, 0].copy_(yf)
+        out_times = torch.tensor(times, dtype=torch.float64, device=dev)
+        seq = 0
+        with torch.cuda.device(dev):
+            stream = _lib.stream_of(yf)
+            while True:
+                _lib.call("tcde_dopri5_linear_attempts", _lib.ptr(control), kind, n_rows, _lib.ptr(knots), _lib.ptr(weight),
+                          _lib.ptr(bias), _lib.ptr(state), _lib.ptr(partials), _lib.ptr(ctl), _lib.ptr(out),
+                          _lib.ptr(out_times), len(times), n_paths, 8, hidden, float(sign), seq, _DEVICE_CHUNK,
+                          _lib.F32, stream)
+                seq += _DEVICE_CHUNK
+                last = ctl[(seq - 1) & 1].cpu()              # the one host read per chunk
+                if last[6] != 0:
+                    break
+                if not math.isfinite(float(last[1])) or float(last[1]) == 0.0 or seq > 10_000_000:
+                    raise RuntimeError("dopri5: step size underflow / non-finite error estimate at t = {}".format(float(last[0])))
+    stats = {"n_accepted": int(last[8]), "n_rejected": int(last[9]), "launches": seq, "device_controlled": True}
+    return out.movedim(1, 0).reshape(len(times), *shape), stats
 
 
 # ------------------------------------------------------------------------- fixed grids (generic)

@@ -32,7 +32,8 @@ constexpr int kC = 8;
 constexpr int kN = kH * kC;       // 256 accumulator columns per tile
 constexpr int kTile = 128;
 constexpr int kTiles = 2;
-constexpr int kThreads = kTile * kTiles;
+constexpr int kRowThreads = kTile * kTiles;     // 256 row threads: thread = path
+constexpr int kIssuerThreads = 128;            // ISSUER variant: one more warpgroup (warp 8 issues, 9-11 only donate registers)
 
 // shared-memory map (bytes).  MODE 0: TF32 hi / lo tiles (K = 32 floats = one 128-byte row each);
 // MODE 1: one FP16 tile per operand, row = [hi(32) | lo(32)] halves = 128 bytes.
@@ -49,8 +50,54 @@ template <int MODE> struct Smem {
     static constexpr int total = bars + 64;
 };
 
-template <int MODE, bool TRACE, bool DUMP>
-__global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a) {
+__device__ __forceinline__ void reg_dealloc_40() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory"); }
+__device__ __forceinline__ void reg_alloc_232() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory"); }
+
+// The MMAs of one tile-stage, issued by ONE thread: D[128 x 256] = split(A) . split(B)^T + bias, then commit -> d_ready
+template <int MODE>
+__device__ __forceinline__ void issue_tile(uint32_t d, unsigned char* smem, unsigned char* a_tile, unsigned char* a_aug, uint64_t* d_ready) {
+    using S = Smem<MODE>;
+    // instruction descriptor: D = F32 (bit 4), A/B format (bits 7 / 10: 2 = TF32, 0 = F16), N >> 3 (bit 17), M >> 4 (bit 24)
+    constexpr uint32_t fmt = (MODE == 0) ? 2u : 0u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+    const uint64_t db = make_desc(smem + S::b);
+    // K-major no-swizzle descriptors: LBO = 128 B (next 16 bytes of K), SBO = 256 B (next 8 rows), version 1
+    const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+    if (MODE == 0) {
+        const uint64_t db_lo = make_desc(smem + S::b + kN * 128);
+        const uint64_t dah = make_desc(a_tile);
+        const uint64_t dal = make_desc(a_tile + kTile * 128);
+        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (0ull << 32) | (1ull << 46);
+        // small terms first; each K block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, db + 2 * kb, idesc, kb > 0);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db_lo + 2 * kb, idesc, 1);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db + 2 * kb, idesc, 1);
+        mma_tf32(d, da_aug, db_aug, idesc, 1);                // + bias (1 * bias_hi + 1 * bias_lo)
+    } else {
+        const uint64_t da = make_desc(a_tile);
+        const uint64_t da_aug = (uint64_t)((smem_u32(a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+        // K block = 16 halves = 32 bytes = +2; A row = [hi: blocks 0,1 | lo: blocks 2,3], B row likewise
+        mma_f16(d, da + 4, db + 0, idesc, 0);                 // z_lo . W_hi
+        mma_f16(d, da + 6, db + 2, idesc, 1);
+        mma_f16(d, da + 0, db + 4, idesc, 1);                 // z_hi . W_lo
+        mma_f16(d, da + 2, db + 6, idesc, 1);
+        mma_f16(d, da + 0, db + 0, idesc, 1);                 // z_hi . W_hi
+        mma_f16(d, da + 2, db + 2, idesc, 1);
+        mma_f16(d, da_aug, db_aug, idesc, 1);                 // + row_scale * bias
+    }
+    mma_commit(d_ready);
+}
+
+// ISSUER = false: 256 threads, lane 0 of each tile's first warp issues its tile's MMAs (255 registers per thread, but the
+// ~650 cycles of issue sit on that warp's chain).  ISSUER = true: 384 threads, warp 8 does nothing but wait and issue;
+// its warpgroup gives its registers to the row warps (setmaxnreg: 40 / 232).
+template <int MODE, bool ISSUER, bool TRACE, bool DUMP>
+__global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1) cdeint_tc_kernel(const UmmaArgs a) {
+    constexpr int kThreads = kRowThreads + (ISSUER ? kIssuerThreads : 0);
+    constexpr int kAllocWarp = ISSUER ? 8 : 0;
     using S = Smem<MODE>;
     using E = exact<float>;
     extern __shared__ unsigned char smem_unaligned[];
@@ -142,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
         }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == kAllocWarp) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -153,7 +200,30 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
 #pragma unroll
     for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
 
-    {
+    if (ISSUER && warp >= kRowThreads / 32) {
+        // ================================ MMA issuer warpgroup ================================
+        reg_dealloc_40();
+        if (warp == kRowThreads / 32) {
+            uint32_t phase[kTiles] = {0, 0};
+            for (int st = 0; st < total; ++st) {
+#pragma unroll
+                for (int t = 0; t < kTiles; ++t) {
+                    if (!tile_live[t]) continue;
+                    mbar_wait(&a_ready[t], phase[t]);
+                    phase[t] ^= 1;
+                    tc_fence_after();
+                    if ((tid & 31) == 0) {
+                        if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+                        issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
+                                         smem + S::a_aug + t * kTile * 32, &d_ready[t]);
+                        if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        if (ISSUER) reg_alloc_232();
         // ================================ row threads =========================================
         const int t = warp >> 2;                          // tile of this thread
         const int r = tid & (kTile - 1);                  // row (path) within the tile
@@ -171,11 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
             const float sign = (a.sign < 0.f) ? -1.f : 1.f;
             float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
 
-            // ---- the tile's MMAs, issued by lane 0 of the tile's first warp once all 128 rows of the operand are in place
-            // instruction descriptor: D = F32 (bit 4), A/B format (bits 7 / 10: 2 = TF32, 0 = F16), N >> 3 (bit 17), M >> 4 (bit 24)
-            constexpr uint32_t fmt = (MODE == 0) ? 2u : 0u;
-            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
-            const bool issuer_warp = (warp & 3) == 0;
+            // ---- ISSUER = false: the tile's MMAs are issued by lane 0 of the tile's first warp once all 128 rows have arrived
+            const bool issuer_warp = !ISSUER && (warp & 3) == 0;
             uint32_t phase_a = 0;
             auto issue_stage = [&](int st) {
                 mbar_wait(&a_ready[t], phase_a);
@@ -183,42 +250,14 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                 tc_fence_after();
                 if ((tid & 31) == 0) {
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
-                    const uint64_t db = make_desc(smem + S::b);
-                    // K-major no-swizzle descriptors: LBO = 128 B (next 16 bytes of K), SBO = 256 B (next 8 rows), version 1
-                    const uint64_t db_aug = (uint64_t)((smem_u32(smem + S::b_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
-                    const uint32_t d = tmem_base + (uint32_t)(t * kN);
-                    if (MODE == 0) {
-                        const uint64_t db_lo = make_desc(smem + S::b + kN * 128);
-                        const uint64_t dah = make_desc(a_tile);
-                        const uint64_t dal = make_desc(a_tile + kTile * 128);
-                        const uint64_t da_aug = (uint64_t)((smem_u32(smem + S::a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (0ull << 32) | (1ull << 46);
-                        // small terms first; each K block is 8 tf32 = 32 bytes = +2 in the descriptor's address field
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dal + 2 * kb, db + 2 * kb, idesc, kb > 0);
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db_lo + 2 * kb, idesc, 1);
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) mma_tf32(d, dah + 2 * kb, db + 2 * kb, idesc, 1);
-                        mma_tf32(d, da_aug, db_aug, idesc, 1);                // + bias (1 * bias_hi + 1 * bias_lo)
-                    } else {
-                        const uint64_t da = make_desc(a_tile);
-                        const uint64_t da_aug = (uint64_t)((smem_u32(a_aug) & 0x3FFFF) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
-                        // K block = 16 halves = 32 bytes = +2; A row = [hi: blocks 0,1 | lo: blocks 2,3], B row likewise
-                        mma_f16(d, da + 4, db + 0, idesc, 0);                 // z_lo . W_hi
-                        mma_f16(d, da + 6, db + 2, idesc, 1);
-                        mma_f16(d, da + 0, db + 4, idesc, 1);                 // z_hi . W_lo
-                        mma_f16(d, da + 2, db + 6, idesc, 1);
-                        mma_f16(d, da + 0, db + 0, idesc, 1);                 // z_hi . W_hi
-                        mma_f16(d, da + 2, db + 2, idesc, 1);
-                        mma_f16(d, da_aug, db_aug, idesc, 1);                 // + row_scale * bias
-                    }
-                    mma_commit(&d_ready[t]);
+                    issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, a_tile, a_aug, &d_ready[t]);
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             };
 
             auto fetch_row = [&](int idx) {               // (b | 2c | 3d) of interval idx -> raw[0..5]
+                if (a.debug & 1) return;
                 const float* src = crow + (int64_t)idx * row_stride;
                 const int parts = cubic ? 6 : 2;
                 for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
@@ -246,13 +285,17 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     }
                 } else {
                     // the path's own power of two: max(|z_k|, bias floor) * s in [2^13, 2^14)
-                    float m = beta;
+                    float mx[8];                          // tree instead of a 32-long dependent chain
 #pragma unroll
-                    for (int k = 0; k < kH; ++k) m = fmaxf(m, fabsf(z[k]));
+                    for (int k = 0; k < 8; ++k)
+                        mx[k] = fmaxf(fmaxf(fabsf(z[k]), fabsf(z[k + 8])), fmaxf(fabsf(z[k + 16]), fabsf(z[k + 24])));
+                    const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                          fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), beta));
                     const int e = min(max(exponent_of(m), 30), 224);
                     const float s = pow2_biased(127 + 13 - (e - 127));
                     inv_scale = pow2_biased(127 - 13 + (e - 127)) * inv_w_scale;
                     const f2 s2 = pk(s, s);
+                    if (!(a.debug & 8)) {
                     uint32_t hi_h[16], lo_h[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -273,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     }
                     const float sb = s * beta;            // <= 2^13 by construction; exact, flushes to 0 far below the row maximum
                     *reinterpret_cast<uint32_t*>(a_aug + aug_off(r, 0)) = pack_h2(sb, sb);
+                    }
                 }
-                fence_proxy_async_smem();
+                if (!(a.debug & 2)) fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[t]);
             };
@@ -355,23 +399,27 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                 // ---- kv[h] = sum_c D[h*C + c] * dX[c]  (the bias is already in D); packed FFMA2, next TMEM
                 //      load in flight while the current 16 columns are consumed
                 float kv[kH];
-                {
-                    uint32_t va[16], vb[16];
-                    tmem_ld16_issue(taddr, va);
+                if (a.debug & 4) {
 #pragma unroll
-                    for (int j = 0; j < kN / 16; ++j) {
+                    for (int h = 0; h < kH; ++h) kv[h] = y[h] * 1e-3f;
+                } else {
+                    // 32-column loads, the next one in flight while the current one is consumed (see umma.cuh)
+                    uint32_t va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int j = 0; j < kN / 32; ++j) {
                         uint32_t* cur = (j & 1) ? vb : va;
-                        tmem_ld16_wait(cur);
-                        if (j + 1 < kN / 16) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
+                        tmem_ld32_wait(cur);
+                        if (j + 1 < kN / 32) tmem_ld32_issue(taddr + (uint32_t)(32 * (j + 1)), (j & 1) ? va : vb);
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
+                        for (int hh = 0; hh < 4; ++hh) {
                             f2 acc = mul2(pk(__uint_as_float(cur[8 * hh + 0]), __uint_as_float(cur[8 * hh + 1])), dx2[0]);
                             acc = fma2(pk(__uint_as_float(cur[8 * hh + 2]), __uint_as_float(cur[8 * hh + 3])), dx2[1], acc);
                             acc = fma2(pk(__uint_as_float(cur[8 * hh + 4]), __uint_as_float(cur[8 * hh + 5])), dx2[2], acc);
                             acc = fma2(pk(__uint_as_float(cur[8 * hh + 6]), __uint_as_float(cur[8 * hh + 7])), dx2[3], acc);
                             float lo, hi;
                             upk(acc, lo, hi);
-                            kv[2 * j + hh] = lo + hi;
+                            kv[4 * j + hh] = lo + hi;
                         }
                     }
                 }
@@ -462,20 +510,20 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == kAllocWarp) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace tc
 
-template <int MODE> static int launch_tc(const UmmaArgs& a, cudaStream_t stream) {
+template <int MODE, bool ISSUER> static int launch_tc(const UmmaArgs& a, cudaStream_t stream) {
     const int64_t per_cta = tc::kTile * tc::kTiles;
     const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
     TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
-    auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, false, true>
-                             : a.trace ? tc::cdeint_tc_kernel<MODE, true, false> : tc::cdeint_tc_kernel<MODE, false, false>;
+    auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, ISSUER, false, true>
+                             : a.trace ? tc::cdeint_tc_kernel<MODE, ISSUER, true, false> : tc::cdeint_tc_kernel<MODE, ISSUER, false, false>;
     constexpr int smem = tc::Smem<MODE>::total + 1024;      // slack for the 1024-byte alignment of the tiles
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)ctas, tc::kThreads, smem, stream>>>(a);
+    kern<<<(unsigned)ctas, tc::kRowThreads + (ISSUER ? tc::kIssuerThreads : 0), smem, stream>>>(a);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }
@@ -487,7 +535,13 @@ int solve_tc_f32(const UmmaArgs& a, int H, int C, int mode, cudaStream_t stream)
                          "tensor-core solve: control, z0 and out must be 16-byte aligned");
     TCDE_CHECK_SUPPORTED(a.stage_dump == nullptr || (reinterpret_cast<uintptr_t>(a.stage_dump) & 15) == 0,
                          "tensor-core solve: the stage dump must be 16-byte aligned");
-    return mode == 1 ? launch_tc<1>(a, stream) : launch_tc<0>(a, stream);
+    // mode: bit 0 = operand split (0 = 3xTF32, 1 = 2xFP16), bit 1 = dedicated issuer warpgroup
+    switch (mode & 3) {
+        case 0: return launch_tc<0, false>(a, stream);
+        case 1: return launch_tc<1, false>(a, stream);
+        case 2: return launch_tc<0, true>(a, stream);
+        default: return launch_tc<1, true>(a, stream);
+    }
 }
 
 }  // namespace tcde

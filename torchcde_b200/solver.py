@@ -653,7 +653,26 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                     # shared-memory budget of the CUDA-core kernel): this package's own stage loop takes any shape
                     pass
             return _generic_solve(X, func, y0, t, method, step_size, is_prod, sig is not None).movedim(-2, 0)
-        return adaptive.odeint_dopri5(fast_field(), y0, times, rtol, atol, options)[0]
+        if (field_params is not None and adaptive.device_dopri5_available(y0, sig[2]) and not options.get("jump_t")
+                and set(options) <= {"first_step", "jump_t"}):
+            # config 4's forward pass: the whole adaptive loop on the device, one launch per attempted step
+            kind = sig[0]
+            control = X._rows() if kind == _lib.CONTROL_CUBIC else X._derivs
+            _check_linear_problem(control, field_params[0], field_params[1], y0)
+            control = control.detach().reshape(-1, control.size(-2), control.size(-1)).contiguous()
+            bias = field_params[1]
+            bias = bias.detach().contiguous() if bias is not None else torch.zeros(
+                field_params[0].size(0), dtype=y0.dtype, device=y0.device)
+            knots = X._t.detach().to(device=y0.device, dtype=y0.dtype).contiguous()
+            out, stats = adaptive.odeint_dopri5_device(control, kind, sig[3], knots, field_params[0].detach().contiguous(), bias,
+                                                       fast_field(), y0, times, rtol, atol, -1.0 if flipped else 1.0,
+                                                       options.get("first_step"))
+            cdeint.last_stats = stats
+            return out
+        out, solver_obj = adaptive.odeint_dopri5(fast_field(), y0, times, rtol, atol, options)
+        cdeint.last_stats = {"n_accepted": solver_obj.n_accepted, "n_rejected": solver_obj.n_rejected,
+                             "device_controlled": False}
+        return out
 
     if not wants_grad:
         with torch.no_grad():
