@@ -85,7 +85,7 @@ def test_gradients_of_the_two_routes_agree():
             # (torchdiffeq's odeint / odeint_adjoint differ in the same way); total and final-time gradients agree
             a, b = torch.stack([a.sum(), a[-1]]), torch.stack([b.sum(), b[-1]])
         # the continuous adjoint discretises the backward ODE itself: agreement to the step error, not to rounding
-        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), (name, float((a - b).abs().max()))
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-4), (name, float((a - b).abs().max()))
 
 
 def test_stacked_paths():

@@ -42,12 +42,13 @@ template <int MODE> struct Smem {
     static constexpr int a_tile_bytes = (MODE == 0 ? 2 : 1) * kTile * 128;          // per tile: hi (+ lo tile in MODE 0)
     static constexpr int b = 0;
     static constexpr int a = b + b_bytes;
-    static constexpr int raw = a + kTiles * a_tile_bytes;                            // [kTiles][6][kTile] float4
-    static constexpr int b_aug = raw + kTiles * 6 * kTile * 16;                      // N rows x 32 B (no swizzle, K-major)
+    static constexpr int raw = a + kTiles * a_tile_bytes;                            // [kTiles][2 buffers][128 rows x 128 B] (TMA, swizzled)
+    static constexpr int raw_buf = kTile * 128;
+    static constexpr int b_aug = raw + kTiles * 2 * raw_buf;                         // N rows x 32 B (no swizzle, K-major)
     static constexpr int a_aug = b_aug + kN * 32;                                    // [kTiles][128 rows x 32 B] (MODE 0: one 8-row group)
     static constexpr int red = a_aug + kTiles * kTile * 32;                          // 64 floats of reduction scratch
-    static constexpr int bars = red + 256;
-    static constexpr int total = bars + 64;
+    static constexpr int bars = red + 256;                                           // a_ready[2], d_ready[2], raw_full[2][2], tmem slot
+    static constexpr int total = bars + 128;
 };
 
 __device__ __forceinline__ void reg_dealloc_40() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory"); }
@@ -95,7 +96,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d, unsigned char* smem, unsi
 // ~650 cycles of issue sit on that warp's chain).  ISSUER = true: 384 threads, warp 8 does nothing but wait and issue;
 // its warpgroup gives its registers to the row warps (setmaxnreg: 40 / 232).
 template <int MODE, bool ISSUER, bool TRACE, bool DUMP>
-__global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1) cdeint_tc_kernel(const UmmaArgs a) {
+__global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1) cdeint_tc_kernel(const UmmaArgs a, const __grid_constant__ CUtensorMap rows_map) {
     constexpr int kThreads = kRowThreads + (ISSUER ? kIssuerThreads : 0);
     constexpr int kAllocWarp = ISSUER ? 8 : 0;
     using S = Smem<MODE>;
@@ -104,8 +105,12 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     uint64_t* a_ready = reinterpret_cast<uint64_t*>(smem + S::bars);
     uint64_t* d_ready = a_ready + kTiles;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + kTiles);
+    uint64_t* raw_full = d_ready + kTiles;                    // [tile][buffer]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 2 * kTiles);
     float* red = reinterpret_cast<float*>(smem + S::red);
+    const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
+    const int row_floats = cubic ? 4 * kC : kC;
+    const uint32_t row_bytes_tile = (uint32_t)(kTile * row_floats * 4);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -186,8 +191,11 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
         for (int t = 0; t < kTiles; ++t) {
             mbar_init(&a_ready[t], kTile);
             mbar_init(&d_ready[t], 1);
+            mbar_init(&raw_full[2 * t], 1);
+            mbar_init(&raw_full[2 * t + 1], 1);
         }
         fence_barrier_init();
+        tma_prefetch_desc(&rows_map);
     }
     if (warp == kAllocWarp) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
@@ -200,11 +208,25 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 #pragma unroll
     for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
 
+    // the spline rows of stage `st` for tile t -> raw[t][st & 1]; completes raw_full[t][st & 1] (one thread calls this)
+    auto fetch_rows = [&](int t, int st) {
+        if (a.debug & 1) return;
+        uint64_t* bar = &raw_full[2 * t + (st & 1)];
+        mbar_expect_tx(bar, row_bytes_tile);
+        tma_load_2d(smem + S::raw + (2 * t + (st & 1)) * S::raw_buf, &rows_map, a.stage_index[st] * row_floats,
+                    (int)(cta_path0 + (int64_t)t * kTile), bar);
+    };
+
     if (ISSUER && warp >= kRowThreads / 32) {
         // ================================ MMA issuer warpgroup ================================
         reg_dealloc_40();
         if (warp == kRowThreads / 32) {
             uint32_t phase[kTiles] = {0, 0};
+            if ((tid & 31) == 0) {
+#pragma unroll
+                for (int t = 0; t < kTiles; ++t)
+                    if (tile_live[t]) fetch_rows(t, 0);
+            }
             for (int st = 0; st < total; ++st) {
 #pragma unroll
                 for (int t = 0; t < kTiles; ++t) {
@@ -216,6 +238,8 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                         if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
                         issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
                                          smem + S::a_aug + t * kTile * 32, &d_ready[t]);
+                        // the rows of the NEXT stage: its buffer was last read two stages ago, before the arrivals just waited for
+                        if (st + 1 < total) fetch_rows(t, st + 1);
                         if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                     }
                     __syncwarp();
@@ -233,11 +257,8 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
         if (tile_live[t]) {
             unsigned char* a_tile = smem + S::a + t * S::a_tile_bytes;
             unsigned char* a_aug = smem + S::a_aug + t * kTile * 32;
-            float4* raw = reinterpret_cast<float4*>(smem + S::raw) + (size_t)t * 6 * kTile + r;
+            const unsigned char* raw_tile = smem + S::raw + 2 * t * S::raw_buf;      // two buffers, stage st in buffer st & 1
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * kN);
-            const bool cubic = (a.control_kind == TCDE_CONTROL_CUBIC);
-            const int row_stride = cubic ? 4 * kC : kC;
-            const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? kC : 0);
             const float sign = (a.sign < 0.f) ? -1.f : 1.f;
             float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
 
@@ -250,19 +271,14 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                 tc_fence_after();
                 if ((tid & 31) == 0) {
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+                    if (st == 0) fetch_rows(t, 0);
                     issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, a_tile, a_aug, &d_ready[t]);
+                    if (st + 1 < total) fetch_rows(t, st + 1);
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
             };
 
-            auto fetch_row = [&](int idx) {               // (b | 2c | 3d) of interval idx -> raw[0..5]
-                if (a.debug & 1) return;
-                const float* src = crow + (int64_t)idx * row_stride;
-                const int parts = cubic ? 6 : 2;
-                for (int j = 0; j < parts; ++j) cp_async16(&raw[j * kTile], src + 4 * j);
-                cp_async_commit();
-            };
             auto write_a = [&](const float* z, int stage_no) {   // next stage input -> split operand rows
                 if (DUMP && live) {                       // ... and, for the adjoint, to the trajectory in HBM
                     float4* dst = reinterpret_cast<float4*>(a.stage_dump + ((int64_t)stage_no * a.n_paths + path) * kH);
@@ -347,7 +363,6 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                 ++jn;
                 next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
             }
-            fetch_row(a.stage_index[0]);
             write_a(y, 0);
             if (issuer_warp) issue_stage(0);
 
@@ -356,25 +371,30 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
             float dt = a.step_dt[0];
             float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
             float frac0 = a.stage_frac[0];                        // this stage's fraction
-            int idx1 = (total > 1) ? a.stage_index[1] : 0;        // next stage's schedule entry
-            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;
+            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;    // next stage's, read a full stage ahead
             uint32_t phase = 0;
             for (int st = 0; st < total; ++st) {
                 const bool more = st + 1 < total;
                 // ---- in the MMA's shadow: dX/dt from the prefetched row (interpolation_cubic.py:331-336), times the
                 //      sign of the time direction and (MODE 1) the inverse of the operand scales
-                cp_async_wait<0>();
+                if (!(a.debug & 1)) mbar_wait(&raw_full[2 * t + (st & 1)], (uint32_t)((st >> 1) & 1));
                 f2 dx2[kC / 2];
                 {
-                    const float4 b0 = raw[0], b1 = raw[kTile];
+                    const unsigned char* rows = raw_tile + (st & 1) * S::raw_buf;
                     if (cubic) {
-                        const float4 c0 = raw[2 * kTile], c1 = raw[3 * kTile], d0 = raw[4 * kTile], d1 = raw[5 * kTile];
+                        // row r of the TMA box = [a | b | 2c | 3d], 16-byte chunk c at position c ^ (r & 7)
+                        const unsigned char* row = rows + r * 128;
+                        const int x = r & 7;
+                        const float4 b0 = *reinterpret_cast<const float4*>(row + ((2 ^ x) << 4)), b1 = *reinterpret_cast<const float4*>(row + ((3 ^ x) << 4));
+                        const float4 c0 = *reinterpret_cast<const float4*>(row + ((4 ^ x) << 4)), c1 = *reinterpret_cast<const float4*>(row + ((5 ^ x) << 4));
+                        const float4 d0 = *reinterpret_cast<const float4*>(row + ((6 ^ x) << 4)), d1 = *reinterpret_cast<const float4*>(row + ((7 ^ x) << 4));
                         const f2 fr = pk(frac0, frac0);
                         dx2[0] = add2(pk(b0.x, b0.y), mul2(add2(pk(c0.x, c0.y), mul2(pk(d0.x, d0.y), fr)), fr));
                         dx2[1] = add2(pk(b0.z, b0.w), mul2(add2(pk(c0.z, c0.w), mul2(pk(d0.z, d0.w), fr)), fr));
                         dx2[2] = add2(pk(b1.x, b1.y), mul2(add2(pk(c1.x, c1.y), mul2(pk(d1.x, d1.y), fr)), fr));
                         dx2[3] = add2(pk(b1.z, b1.w), mul2(add2(pk(c1.z, c1.w), mul2(pk(d1.z, d1.w), fr)), fr));
                     } else {
+                        const float4 b0 = *reinterpret_cast<const float4*>(rows + r * 32), b1 = *reinterpret_cast<const float4*>(rows + r * 32 + 16);
                         dx2[0] = pk(b0.x, b0.y); dx2[1] = pk(b0.z, b0.w); dx2[2] = pk(b1.x, b1.y); dx2[3] = pk(b1.z, b1.w);
                     }
                     const float post = sign * inv_scale;          // +-1 in MODE 0; a power of two (exact) in MODE 1
@@ -382,12 +402,8 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dx2[q] = mul2(dx2[q], p2);
                 }
-                if (more) fetch_row(idx1);
                 frac0 = frac1;
-                if (st + 2 < total) {                     // schedule entries are read a full stage ahead
-                    idx1 = a.stage_index[st + 2];
-                    frac1 = a.stage_frac[st + 2];
-                }
+                if (st + 2 < total) frac1 = a.stage_frac[st + 2];
 
                 const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
                 if (tr) a.trace[st * 8 + 2] = clock64();
@@ -523,7 +539,12 @@ template <int MODE, bool ISSUER> static int launch_tc(const UmmaArgs& a, cudaStr
                              : a.trace ? tc::cdeint_tc_kernel<MODE, ISSUER, true, false> : tc::cdeint_tc_kernel<MODE, ISSUER, false, false>;
     constexpr int smem = tc::Smem<MODE>::total + 1024;      // slack for the 1024-byte alignment of the tiles
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(unsigned)ctas, tc::kRowThreads + (ISSUER ? tc::kIssuerThreads : 0), smem, stream>>>(a);
+    alignas(64) CUtensorMap rows_map;
+    const int row_floats = (a.control_kind == TCDE_CONTROL_CUBIC) ? 4 * tc::kC : tc::kC;
+    const int rc = tc::make_rows_tensor_map(&rows_map, a.control, a.n_paths, a.n_rows, row_floats);
+    TCDE_CHECK_SUPPORTED(rc == 0, "tensor-core solve: cuTensorMapEncodeTiled failed (%d) for control [%lld][%lld x %d floats]", rc,
+                         (long long)a.n_paths, (long long)a.n_rows, row_floats);
+    kern<<<(unsigned)ctas, tc::kRowThreads + (ISSUER ? tc::kIssuerThreads : 0), smem, stream>>>(a, rows_map);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }

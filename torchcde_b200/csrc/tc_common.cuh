@@ -1,5 +1,6 @@
 // FP16-split helpers shared by the round-2 tensor-core kernels (solve_tc.cu, solve_dopri5.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "umma.cuh"
@@ -34,6 +35,48 @@ __device__ __forceinline__ float pow2_biased(int e) { return __uint_as_float((ui
 // the two K chunks 128 B apart (LBO), rows 16 B apart
 __device__ __forceinline__ uint32_t aug_off(int row, int chunk) { return (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16); }
 
+
+// ---- TMA (cp.async.bulk.tensor, SASS UTMALDG): the spline rows of one interval for the 128 paths of a tile ------------
+// The control is a 2-D tensor [paths][n_rows * row_floats] (row stride = one path's whole coefficient block); a box of
+// {row_floats, 128 paths} at coordinates (interval * row_floats, first path) is the 128 rows x 128 bytes (cubic, 8
+// channels: a | b | 2c | 3d) that one Runge-Kutta stage of a tile reads.  One thread issues the copy; the bytes land in
+// shared memory with the 128-byte swizzle (16-byte chunk c of row r at position c ^ (r & 7)): every thread then reads
+// its own row with conflict-free 128-bit loads.  Rows beyond the batch are zero-filled by the TMA unit.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// host: the tensor map of a control tensor (float32).  cuTensorMapEncodeTiled is taken from the driver through the runtime
+// (no link-time dependency on libcuda).  Returns cudaSuccess or an error.
+inline int make_rows_tensor_map(CUtensorMap* map, const float* control, int64_t n_paths, int64_t n_rows, int row_floats) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)(n_rows * row_floats), (cuuint64_t)n_paths};
+    const cuuint64_t strides[1] = {(cuuint64_t)(n_rows * row_floats) * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)row_floats, 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUtensorMapSwizzle swz = (row_floats * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(control), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
 
 // ---- building blocks of a [128 paths x 32 hidden] . [32 x 256] tile product with the 2xFP16 operand split ------------
 constexpr int kHid = 32, kCh = 8, kCols = kHid * kCh, kRows = 128;
