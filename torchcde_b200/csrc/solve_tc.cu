@@ -209,41 +209,39 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
     for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
 
     // the spline rows of stage `st` for tile t -> raw[t][st & 1]; completes raw_full[t][st & 1] (one thread calls this)
-    auto fetch_rows = [&](int t, int st) {
+    auto fetch_rows = [&](int t, int st, int interval) {
         if (a.debug & 1) return;
         uint64_t* bar = &raw_full[2 * t + (st & 1)];
         mbar_expect_tx(bar, row_bytes_tile);
-        tma_load_2d(smem + S::raw + (2 * t + (st & 1)) * S::raw_buf, &rows_map, a.stage_index[st] * row_floats,
+        tma_load_2d(smem + S::raw + (2 * t + (st & 1)) * S::raw_buf, &rows_map, interval * row_floats,
                     (int)(cta_path0 + (int64_t)t * kTile), bar);
     };
 
     if (ISSUER && warp >= kRowThreads / 32) {
         // ================================ MMA issuer warpgroup ================================
         reg_dealloc_40();
-        if (warp == kRowThreads / 32) {
-            uint32_t phase[kTiles] = {0, 0};
-            if ((tid & 31) == 0) {
-#pragma unroll
-                for (int t = 0; t < kTiles; ++t)
-                    if (tile_live[t]) fetch_rows(t, 0);
-            }
+        // one issuer warp PER TILE (warps 8 and 9): a tile's MMAs start as soon as its own 128 rows have arrived, whatever the
+        // other tile's issuer is doing (one warp serving both tiles serialised them: 2 x ~1,250 cycles per stage)
+        const int t = warp - kRowThreads / 32;
+        if (t < kTiles && tile_live[t]) {
+            uint32_t phase = 0;
+            int idx_next = (total > 1) ? a.stage_index[1] : 0;          // schedule entries are read a stage ahead of their use
+            if ((tid & 31) == 0) fetch_rows(t, 0, a.stage_index[0]);
             for (int st = 0; st < total; ++st) {
-#pragma unroll
-                for (int t = 0; t < kTiles; ++t) {
-                    if (!tile_live[t]) continue;
-                    mbar_wait(&a_ready[t], phase[t]);
-                    phase[t] ^= 1;
-                    tc_fence_after();
-                    if ((tid & 31) == 0) {
-                        if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
-                        issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
-                                         smem + S::a_aug + t * kTile * 32, &d_ready[t]);
-                        // the rows of the NEXT stage: its buffer was last read two stages ago, before the arrivals just waited for
-                        if (st + 1 < total) fetch_rows(t, st + 1);
-                        if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
-                    }
-                    __syncwarp();
+                const int idx_fetch = idx_next;
+                if (st + 2 < total) idx_next = a.stage_index[st + 2];
+                mbar_wait(&a_ready[t], phase);
+                phase ^= 1;
+                tc_fence_after();
+                if ((tid & 31) == 0) {
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+                    issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
+                                     smem + S::a_aug + t * kTile * 32, &d_ready[t]);
+                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
+                    // the rows of the NEXT stage: its buffer was last read two stages ago, before the arrivals just waited for
+                    if (st + 1 < total) fetch_rows(t, st + 1, idx_fetch);
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -265,15 +263,18 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
             // ---- ISSUER = false: the tile's MMAs are issued by lane 0 of the tile's first warp once all 128 rows have arrived
             const bool issuer_warp = !ISSUER && (warp & 3) == 0;
             uint32_t phase_a = 0;
+            int idx_issue = (total > 1) ? a.stage_index[1] : 0;
             auto issue_stage = [&](int st) {
+                const int idx_fetch = idx_issue;
+                if (st + 2 < total) idx_issue = a.stage_index[st + 2];
                 mbar_wait(&a_ready[t], phase_a);
                 phase_a ^= 1;
                 tc_fence_after();
                 if ((tid & 31) == 0) {
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
-                    if (st == 0) fetch_rows(t, 0);
+                    if (st == 0) fetch_rows(t, 0, a.stage_index[0]);
                     issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, a_tile, a_aug, &d_ready[t]);
-                    if (st + 1 < total) fetch_rows(t, st + 1);
+                    if (st + 1 < total) fetch_rows(t, st + 1, idx_fetch);
                     if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
                 }
                 __syncwarp();
