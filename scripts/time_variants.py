@@ -15,7 +15,7 @@ torch.manual_seed(1)
 func = cde.LinearVectorField(H, C).to(dev)
 t = torch.tensor([0.0, L - 1.0])
 opts = {"step_size": 1.0}
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,3,4").split(",")]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,3,4,260").split(",")]
 with torch.no_grad():
     coeffs = cde.hermite_cubic_coefficients_with_backward_differences(x)
     X = cde.CubicSpline(coeffs)

@@ -109,7 +109,8 @@ struct UmmaArgs {
     float sign;
     long long* trace;     // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
     float* stage_dump;    // optional [n_steps * n_stages][n_paths][32]: the input of every stage (for the adjoint)
-    int debug;            // profiling experiments of solve_tc.cu (WRONG results): 1 no row fetch, 2 no proxy fence, 4 no TMEM reads, 8 no split
+    int debug;            // solve_tc.cu: profiling experiments with WRONG results (1 no row fetch, 2 no proxy fence, 4 no TMEM reads,
+                          // 8 no split) and scheduling switches with right results (16 one segment, 32 force four segments)
 };
 bool solve_umma_supported(int H, int C);
 int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);

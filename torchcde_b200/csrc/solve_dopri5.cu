@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             mbar_wait(&d_ready[t_], phase_d);
             phase_d ^= 1;
             tc_fence_after();
-            contract_row(taddr, dx2, kv);
+            contract_row<32>(taddr, dx2, kv);
         };
         auto nothing = [] {};
 

@@ -502,7 +502,7 @@ static int launch_field(const void* control, int control_kind, int64_t n_rows, c
 
 // ---- tensor-core variant (solve_umma.cu) -------------------------------------------------------
 #ifndef TCDE_DEFAULT_TC_MODE
-#define TCDE_DEFAULT_TC_MODE 3      // bit 0: 2xFP16 operand split (7 MMAs per stage) instead of 3xTF32 (13); bit 1: dedicated issuer warpgroup
+#define TCDE_DEFAULT_TC_MODE 1      // bit 0: 2xFP16 operand split (7 MMAs per stage) instead of 3xTF32 (13)
 #endif
 static long long* g_trace = nullptr;   // profiling aid: device buffer for in-kernel clock stamps (see tcde_set_trace_buffer)
 static int g_debug_flags = 0;
@@ -520,8 +520,8 @@ extern "C" int tcde_set_trace_buffer(void* device_buffer) {
 
 extern "C" int tcde_set_solve_variant(int variant) {
     TCDE_CHECK_ARG(variant >= 0 && (variant & 15) <= 6,
-                   "variant=%d (0 auto, 1 CUDA-core kernel, 2 tcgen05 round-1 kernel, 3 / 4 round-2 kernel 3xTF32 / 2xFP16 with the "
-                   "tile's own first warp issuing, 5 / 6 = 2xFP16 / 3xTF32 with a dedicated issuer warpgroup)", variant);
+                   "variant=%d (0 auto, 1 CUDA-core kernel, 2 tcgen05 round-1 kernel, 3 / 4 round-2 kernel with the 3xTF32 / 2xFP16 "
+                   "operand split; 6 / 5 are aliases of 3 / 4)", variant);
     g_solve_variant = variant & 15;
     g_debug_flags = variant >> 4;        // profiling experiments (timing only, wrong results); 0 in normal use
     return TCDE_OK;
@@ -576,8 +576,9 @@ static int solve_fixed_linear(const void* control, int control_kind, int64_t n_r
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
                        (int)n_out, (float)sign, g_trace, (float*)stage_dump, g_debug_flags};
             if (g_solve_variant == 2 || g_solve_variant == 0) return solve_umma_f32(u, (int)hidden, (int)channels, s);   // TODO r2: auto -> solve_tc once validated on the GPU
-            const int mode = g_solve_variant == 3 ? 0 : g_solve_variant == 4 ? 1 : g_solve_variant == 5 ? 3 : g_solve_variant == 6 ? 2
-                                                                                                                      : TCDE_DEFAULT_TC_MODE;
+            // round-2 kernel: 3 / 6 = 3xTF32 split, 4 / 5 = 2xFP16 split (5, 6: aliases from the development history)
+            const int mode = (g_solve_variant == 3 || g_solve_variant == 6) ? 0 : (g_solve_variant == 4 || g_solve_variant == 5) ? 1
+                                                                                                                                  : TCDE_DEFAULT_TC_MODE;
             return solve_tc_f32(u, (int)hidden, (int)channels, mode, s);
         }
         TCDE_CHECK_SUPPORTED(stage_dump == nullptr, "the stage dump is written by the tensor-core solve only "

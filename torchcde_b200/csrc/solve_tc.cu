@@ -1,24 +1,32 @@
-// Hot path (ii), round 2: the fused fixed-step CDE solve on tcgen05 with the Runge-Kutta state in registers.
+// Hot path (ii), round 2: the fused fixed-step CDE solve on tcgen05 -- persistent, balanced, warp-specialised.
 //
-// What changed against solve_umma.cu (round 1, kept as variant 2) and why -- profiles/r01_umma_trace.txt showed one
-// tile-stage as a 4,065-cycle serial chain of which only 1,664 are tensor work (13 MMAs x 128 cycles: the issue loop
-// finishes after ~1,330 because the MMA queue holds the last three), so two ping-ponging tiles kept the pipe 82 % busy:
-//   * the slopes k1 and k2 (+k3) never leave registers (one CTA per SM: the register file is there to be used): the
-//     64 LDS + 32-64 STS per thread and stage of the old "park" and their latency are gone;
-//   * MODE 1 halves the tensor work itself: operands are split into TWO FP16 pieces instead of two TF32 pieces.  An
-//     FP16 MMA carries K = 16 per instruction at the cycle cost of a K = 8 TF32 one, so the three partial products
-//     z_lo.W_hi + z_hi.W_lo + z_hi.W_hi are 6 MMAs instead of 12 (+1 for the bias in both modes).  FP16 has the same
-//     11-bit significand as TF32 (hi + lo = 22 bits, error ~2^-22 like 3xTF32) but only 5 exponent bits, so every
-//     path's row is scaled by its own power of two (exact) so that max(|z_k|, bias floor) lands in [2^13, 2^14); the
-//     weights get one global power of two; elements more than 2^-27 below the row maximum lose relative -- not
-//     absolute -- precision, which is what a dot product needs.  The scale is undone for free by folding its inverse
-//     into the path's dX/dt before the contraction.  hi | lo of a row share ONE 128-byte swizzled A row (K = 64).
+// What changed against solve_umma.cu (round 1, kept as variant 2), each step measured (profiles/r02_*):
+//   * r01 trace: one tile-stage was a 4,065-cycle serial chain of which 1,664 are tensor work (13 MMAs x 128 cycles), and
+//     256 CTAs on 148 SMs ran as 1.73 waves.  The chain, not the tensor pipe, sets the pace (two tiles of 128 paths is all
+//     that TMEM's 512 columns allow in flight), so every change below shortens the chain or removes work from it:
+//   * the Runge-Kutta slopes k1, k2 (+k3) never leave registers: the row warps get 240 registers by setmaxnreg from a third
+//     warpgroup (warps 8, 9 = one MMA issuer per tile; 10, 11 only donate); the old 64 LDS + 32-64 STS per thread and
+//     stage of "parked" slopes are gone;
+//   * MODE 1 halves the tensor work: operands are split into TWO FP16 pieces instead of two TF32 pieces.  An FP16 MMA
+//     carries K = 16 per instruction at the cycle cost of a K = 8 TF32 one, so z_lo.W_hi + z_hi.W_lo + z_hi.W_hi are
+//     6 MMAs instead of 12 (+1 for the bias in both modes).  FP16 has TF32's 11-bit significand (hi + lo = 22 bits,
+//     error ~2^-22 like 3xTF32) but only 5 exponent bits, so every path's row is scaled by its own power of two (exact)
+//     so that max(|z_k|, bias floor) lands in [2^13, 2^14); the weights get one global power of two; elements more than
+//     2^-27 below the row maximum lose relative -- not absolute -- precision, which is what a dot product needs.  The
+//     scale is undone for free by folding its inverse into the path's dX/dt before the contraction.  hi | lo of a row
+//     share ONE 128-byte swizzled A row (K = 64);
+//   * the spline rows come by TMA: one cp.async.bulk.tensor per tile and stage (box = 128 paths x one interval's
+//     a|b|2c|3d, 128B swizzle, double buffered, issued by the tile's MMA issuer a stage ahead).  The per-thread cp.async
+//     of round 1 touched 32 cache lines per warp instruction: 1,536 L1 cycles per stage on the SM's one LSU pipe;
+//   * 32-column TMEM loads (the next in flight while the current is contracted), a tree for the row maximum;
+//   * persistent CTAs (one per SM) over work units (pair of tiles, segment of the time axis): 256 pairs x 4 segments over
+//     148 SMs is 6.9 -> 7 rounds of a quarter solve = 1.75 solves per SM instead of 2.  A unit starts from the state its
+//     predecessor left in HBM (32 floats per path) once that unit's flag is up; units are dealt round-robin in
+//     (segment, pair) order, so a predecessor is always a full round older and nobody waits in steady state.
 //
-//   * no dedicated issuer warp: 9 warps are allocated like 12 (168 registers per thread), 8 warps get 255.  Lane 0 of a
-//     tile's first warp issues the tile's MMAs as soon as the tile's 128 rows have arrived on a_ready[t].
-//
-// CTA anatomy: two tiles of 128 paths, thread = path (256 threads); accumulators [128 x 256] fp32 per tile in TMEM (all
-// 512 columns); a_ready[t] (128 arrivals) / d_ready[t] (tcgen05.commit) mbarriers.
+// CTA anatomy (384 threads): warps 0-3 / 4-7 = the 128 rows of tile 0 / 1 (thread = path); warp 8 / 9 = MMA + TMA
+// issuer of tile 0 / 1; accumulators [128 x 256] fp32 per tile in TMEM (all 512 columns).  mbarriers: a_ready[t]
+// (128 arrivals: operand rows written), d_ready[t] (tcgen05.commit), raw_full[t][2] (TMA bytes landed).
 #include "tc_common.cuh"
 
 namespace tcde {
@@ -33,7 +41,19 @@ constexpr int kN = kH * kC;       // 256 accumulator columns per tile
 constexpr int kTile = 128;
 constexpr int kTiles = 2;
 constexpr int kRowThreads = kTile * kTiles;     // 256 row threads: thread = path
-constexpr int kIssuerThreads = 128;            // ISSUER variant: one more warpgroup (warp 8 issues, 9-11 only donate registers)
+constexpr int kThreads = kRowThreads + 128;     // + the issuer warpgroup
+#ifndef TCDE_TC_LD_WIDTH
+#define TCDE_TC_LD_WIDTH 16                     // columns per TMEM load in the contraction (32 does not fit 240 registers)
+#endif
+
+// how the time axis is cut and where the hand-over state lives (all device pointers; n_seg == 1: nothing is handed over)
+struct Units {
+    int n_seg;
+    int steps_per_seg;
+    const int32_t* seg_first_out;   // [n_seg]: first output index whose step is >= the segment's first step
+    float* ystate;                  // [n_paths][32]: state at the end of a path's last finished segment
+    int* progress;                  // [n_pairs]: segments finished, zero before the launch
+};
 
 // shared-memory map (bytes).  MODE 0: TF32 hi / lo tiles (K = 32 floats = one 128-byte row each);
 // MODE 1: one FP16 tile per operand, row = [hi(32) | lo(32)] halves = 128 bytes.
@@ -51,8 +71,14 @@ template <int MODE> struct Smem {
     static constexpr int total = bars + 128;
 };
 
-__device__ __forceinline__ void reg_dealloc_40() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n" ::: "memory"); }
-__device__ __forceinline__ void reg_alloc_232() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n" ::: "memory"); }
+__device__ __forceinline__ void reg_dealloc_24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::: "memory"); }
+__device__ __forceinline__ void reg_alloc_240() { asm volatile("setmaxnreg.inc.sync.aligned.u32 240;\n" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // The MMAs of one tile-stage, issued by ONE thread: D[128 x 256] = split(A) . split(B)^T + bias, then commit -> d_ready
 template <int MODE>
@@ -92,13 +118,8 @@ __device__ __forceinline__ void issue_tile(uint32_t d, unsigned char* smem, unsi
     mma_commit(d_ready);
 }
 
-// ISSUER = false: 256 threads, lane 0 of each tile's first warp issues its tile's MMAs (255 registers per thread, but the
-// ~650 cycles of issue sit on that warp's chain).  ISSUER = true: 384 threads, warp 8 does nothing but wait and issue;
-// its warpgroup gives its registers to the row warps (setmaxnreg: 40 / 232).
-template <int MODE, bool ISSUER, bool TRACE, bool DUMP>
-__global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1) cdeint_tc_kernel(const UmmaArgs a, const __grid_constant__ CUtensorMap rows_map) {
-    constexpr int kThreads = kRowThreads + (ISSUER ? kIssuerThreads : 0);
-    constexpr int kAllocWarp = ISSUER ? 8 : 0;
+template <int MODE, bool TRACE, bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a, const Units un, const __grid_constant__ CUtensorMap rows_map) {
     using S = Smem<MODE>;
     using E = exact<float>;
     extern __shared__ unsigned char smem_unaligned[];
@@ -114,32 +135,10 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int64_t cta_path0 = (int64_t)blockIdx.x * (kTile * kTiles);
-    const int total = a.n_steps * a.n_stages;
+    constexpr int kAllocWarp = kRowThreads / 32;              // warp 8
 
     // ---- one-time setup: operand B (the weights, split) and the bias K-block -------------------------------------
-    float w_scale = 1.f, inv_w_scale = 1.f, beta = 0.f;       // MODE 1: global power-of-two scales
-    if (MODE == 1) {
-        float wmax = 0.f, bmax = 0.f;
-        for (int e = tid; e < kN * kH; e += kThreads) wmax = fmaxf(wmax, fabsf(a.weight[e]));
-        for (int e = tid; e < kN; e += kThreads) bmax = fmaxf(bmax, fabsf(a.bias[e]));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-            bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-        }
-        if ((tid & 31) == 0) { red[warp] = wmax; red[16 + warp] = bmax; }
-        __syncthreads();
-        wmax = 0.f; bmax = 0.f;
-        for (int w = 0; w < kThreads / 32; ++w) { wmax = fmaxf(wmax, red[w]); bmax = fmaxf(bmax, red[16 + w]); }
-        // exponents clamped so that every derived power of two is a normal fp32 number; an all-zero weight takes the
-        // bias's exponent (the product is then the bias alone)
-        const int eb = min(max(exponent_of(bmax), 40), 215);
-        const int ew = (wmax > 0.f) ? min(max(exponent_of(wmax), 40), 215) : (bmax > 0.f ? eb : 127);
-        w_scale = pow2_biased(127 + 13 - (ew - 127));                                // max |W| * w_scale in [2^13, 2^14)
-        inv_w_scale = pow2_biased(127 - 13 + (ew - 127));
-        if (bmax > 0.f) beta = pow2_biased(min(max(127 + eb - ew, 2), 250));         // 2^(ex(bmax) - ex(wmax))
-    }
+    float inv_w_scale = 1.f, beta = 0.f;                      // MODE 1: global power-of-two scales
     if (MODE == 0) {
         float* b_hi = reinterpret_cast<float*>(smem + S::b);
         float* b_lo = b_hi + kN * 32;
@@ -163,29 +162,10 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
             b_aug[(row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3)] = (k == 0) ? hi : (k == 1) ? (bv - hi) : 0.f;
         }
     } else {
-        __half* bt = reinterpret_cast<__half*>(smem + S::b);
-        for (int e = tid; e < kN * kH; e += kThreads) {
-            const int n = e >> 5, k = e & 31;
-            const float w = a.weight[e] * w_scale;
-            const __half hi = __float2half_rn(w);
-            const __half lo = __float2half_rn(w - __half2float(hi));
-            // row n = 128 bytes: halves 0..31 = hi, 32..63 = lo; 16-byte chunk c (8 halves) sits at c ^ (n & 7)
-            bt[n * 64 + ((((k >> 3)) ^ (n & 7)) << 3) + (k & 7)] = hi;
-            bt[n * 64 + ((((k >> 3) + 4) ^ (n & 7)) << 3) + (k & 7)] = lo;
-        }
-        unsigned char* b_aug = smem + S::b_aug;
-        unsigned char* a_aug = smem + S::a_aug;
-        const float bias_scale = (beta > 0.f) ? w_scale / beta : 0.f;                // bias * w_scale / beta in [2^13, 2^14)
-        for (int row = tid; row < kN; row += kThreads) {
-            const float bv = a.bias[row] * bias_scale;
-            const __half hi = __float2half_rn(bv);
-            const __half lo = __float2half_rn(bv - __half2float(hi));
-            uint4 c0 = make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(b_aug + aug_off(row, 0)) = c0;
-            *reinterpret_cast<uint4*>(b_aug + aug_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-        }
+        float w_scale;
+        prepare_b_fp16(smem + S::b, smem + S::b_aug, a.weight, a.bias, red, tid, kThreads, w_scale, inv_w_scale, beta);
         for (int e = tid; e < kTiles * kTile * 2; e += kThreads)                     // per-row scale goes to k = 0, 1 each stage
-            *reinterpret_cast<uint4*>(a_aug + (e >> 8) * (kTile * 32) + aug_off((e >> 1) & 127, e & 1)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(smem + S::a_aug + (e >> 8) * (kTile * 32) + aug_off((e >> 1) & 127, e & 1)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         for (int t = 0; t < kTiles; ++t) {
@@ -204,81 +184,82 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    bool tile_live[kTiles];
-#pragma unroll
-    for (int t = 0; t < kTiles; ++t) tile_live[t] = (cta_path0 + (int64_t)t * kTile) < a.n_paths;
+    const bool is_row = warp < kRowThreads / 32;
+    const int n_pairs = (int)((a.n_paths + kRowThreads - 1) / kRowThreads);
+    const int n_units = n_pairs * un.n_seg;
+    const int t = is_row ? (warp >> 2) : (warp - kRowThreads / 32);      // tile served by this warp (issuers: 0, 1; donors: 2, 3)
+    const int r = tid & (kTile - 1);
+    uint32_t phase_a = 0, phase_d = 0;                       // issuer / row side of the two hand-shakes
+    uint32_t kcount = 0;                                     // stages this warp's tile has gone through: raw buffer kcount & 1
 
-    // the spline rows of stage `st` for tile t -> raw[t][st & 1]; completes raw_full[t][st & 1] (one thread calls this)
-    auto fetch_rows = [&](int t, int st, int interval) {
-        if (a.debug & 1) return;
-        uint64_t* bar = &raw_full[2 * t + (st & 1)];
-        mbar_expect_tx(bar, row_bytes_tile);
-        tma_load_2d(smem + S::raw + (2 * t + (st & 1)) * S::raw_buf, &rows_map, interval * row_floats,
-                    (int)(cta_path0 + (int64_t)t * kTile), bar);
-    };
+    // the two roles run the SAME unit loop (same CTA barriers per unit) in separate code regions: setmaxnreg gives each
+    // region its own register budget
+#define TCDE_UNIT_PROLOGUE()                                                                                          \
+        const int seg = u / n_pairs, pair = u - seg * n_pairs;                                                        \
+        const int step_lo = seg * un.steps_per_seg;                                                                   \
+        const int step_hi = min(a.n_steps, step_lo + un.steps_per_seg);                                               \
+        const int st_lo = step_lo * a.n_stages, st_hi = step_hi * a.n_stages;                                         \
+        const int64_t tile_path0 = (int64_t)pair * kRowThreads + (int64_t)t * kTile;                                  \
+        const bool tile_live = t < kTiles && tile_path0 < a.n_paths;                                                  \
+        if (seg > 0) {                      /* the unit that ends where this one starts must be done */              \
+            if (tid == 0)                                                                                             \
+                while (ld_acquire(un.progress + pair) < seg) __nanosleep(64);                                         \
+            __syncthreads();                                                                                          \
+        }
+#define TCDE_UNIT_EPILOGUE()                                                                                          \
+        if (seg + 1 < un.n_seg) {                                                                                     \
+            __syncthreads();                                                                                          \
+            if (tid == 0) st_release(un.progress + pair, seg + 1);                                                    \
+        }
 
-    if (ISSUER && warp >= kRowThreads / 32) {
-        // ================================ MMA issuer warpgroup ================================
-        reg_dealloc_40();
-        // one issuer warp PER TILE (warps 8 and 9): a tile's MMAs start as soon as its own 128 rows have arrived, whatever the
-        // other tile's issuer is doing (one warp serving both tiles serialised them: 2 x ~1,250 cycles per stage)
-        const int t = warp - kRowThreads / 32;
-        if (t < kTiles && tile_live[t]) {
-            uint32_t phase = 0;
-            int idx_next = (total > 1) ? a.stage_index[1] : 0;          // schedule entries are read a stage ahead of their use
-            if ((tid & 31) == 0) fetch_rows(t, 0, a.stage_index[0]);
-            for (int st = 0; st < total; ++st) {
-                const int idx_fetch = idx_next;
-                if (st + 2 < total) idx_next = a.stage_index[st + 2];
-                mbar_wait(&a_ready[t], phase);
-                phase ^= 1;
-                tc_fence_after();
-                if ((tid & 31) == 0) {
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
+    if (!is_row) {
+        reg_dealloc_24();
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            TCDE_UNIT_PROLOGUE()
+            // ================================ MMA + TMA issuer of tile t ==========================
+            if (tile_live && (tid & 31) == 0) {
+                auto fetch_rows = [&](uint32_t k, int interval) {     // rows of one interval -> raw[t][k & 1]
+                    if (a.debug & 1) return;
+                    uint64_t* bar = &raw_full[2 * t + (k & 1)];
+                    mbar_expect_tx(bar, row_bytes_tile);
+                    tma_load_2d(smem + S::raw + (2 * t + (k & 1)) * S::raw_buf, &rows_map, interval * row_floats, (int)tile_path0, bar);
+                };
+                int idx_next = (st_lo + 1 < st_hi) ? a.stage_index[st_lo + 1] : 0;   // schedule entries are read a stage ahead
+                fetch_rows(kcount, a.stage_index[st_lo]);
+                for (int st = st_lo; st < st_hi; ++st) {
+                    const int idx_fetch = idx_next;
+                    if (st + 2 < st_hi) idx_next = a.stage_index[st + 2];
+                    mbar_wait(&a_ready[t], phase_a);
+                    phase_a ^= 1;
+                    tc_fence_after();
+                    const bool tr = TRACE && a.trace && u == 0 && t == 0 && st < 64;
+                    if (tr) a.trace[st * 8 + 0] = clock64();
                     issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
                                      smem + S::a_aug + t * kTile * 32, &d_ready[t]);
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
-                    // the rows of the NEXT stage: its buffer was last read two stages ago, before the arrivals just waited for
-                    if (st + 1 < total) fetch_rows(t, st + 1, idx_fetch);
+                    if (tr) a.trace[st * 8 + 1] = clock64();
+                    ++kcount;
+                    // the rows of the NEXT stage: their buffer was last read two stages ago, before the arrivals just waited for
+                    if (st + 1 < st_hi) fetch_rows(kcount, idx_fetch);
                 }
-                __syncwarp();
             }
+            __syncwarp();                                     // lanes 1-31 wait here for lane 0: the CTA barriers below are warp-aligned
+            TCDE_UNIT_EPILOGUE()
         }
     } else {
-        if (ISSUER) reg_alloc_232();
-        // ================================ row threads =========================================
-        const int t = warp >> 2;                          // tile of this thread
-        const int r = tid & (kTile - 1);                  // row (path) within the tile
-        const int64_t path = cta_path0 + (int64_t)t * kTile + r;
-        const bool live = path < a.n_paths;
-        const int64_t lpath = live ? path : a.n_paths - 1;
-        if (tile_live[t]) {
+        reg_alloc_240();
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            TCDE_UNIT_PROLOGUE()
+            if (tile_live) {
+            // ================================ row threads =========================================
+            const int64_t path = tile_path0 + r;
+            const bool live = path < a.n_paths;
+            const int64_t lpath = live ? path : a.n_paths - 1;
             unsigned char* a_tile = smem + S::a + t * S::a_tile_bytes;
             unsigned char* a_aug = smem + S::a_aug + t * kTile * 32;
-            const unsigned char* raw_tile = smem + S::raw + 2 * t * S::raw_buf;      // two buffers, stage st in buffer st & 1
+            const unsigned char* raw_tile = smem + S::raw + 2 * t * S::raw_buf;      // two buffers
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * kN);
             const float sign = (a.sign < 0.f) ? -1.f : 1.f;
             float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
-
-            // ---- ISSUER = false: the tile's MMAs are issued by lane 0 of the tile's first warp once all 128 rows have arrived
-            const bool issuer_warp = !ISSUER && (warp & 3) == 0;
-            uint32_t phase_a = 0;
-            int idx_issue = (total > 1) ? a.stage_index[1] : 0;
-            auto issue_stage = [&](int st) {
-                const int idx_fetch = idx_issue;
-                if (st + 2 < total) idx_issue = a.stage_index[st + 2];
-                mbar_wait(&a_ready[t], phase_a);
-                phase_a ^= 1;
-                tc_fence_after();
-                if ((tid & 31) == 0) {
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 0] = clock64();
-                    if (st == 0) fetch_rows(t, 0, a.stage_index[0]);
-                    issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, a_tile, a_aug, &d_ready[t]);
-                    if (st + 1 < total) fetch_rows(t, st + 1, idx_fetch);
-                    if (TRACE && a.trace && blockIdx.x == 0 && t == 0 && st < 64) a.trace[st * 8 + 1] = clock64();
-                }
-                __syncwarp();
-            };
 
             auto write_a = [&](const float* z, int stage_no) {   // next stage input -> split operand rows
                 if (DUMP && live) {                       // ... and, for the adjoint, to the trajectory in HBM
@@ -300,40 +281,8 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                         *reinterpret_cast<float4*>(a_hi + off) = hi;
                         *reinterpret_cast<float4*>(a_lo + off) = lo;
                     }
-                } else {
-                    // the path's own power of two: max(|z_k|, bias floor) * s in [2^13, 2^14)
-                    float mx[8];                          // tree instead of a 32-long dependent chain
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        mx[k] = fmaxf(fmaxf(fabsf(z[k]), fabsf(z[k + 8])), fmaxf(fabsf(z[k + 16]), fabsf(z[k + 24])));
-                    const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                                          fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), beta));
-                    const int e = min(max(exponent_of(m), 30), 224);
-                    const float s = pow2_biased(127 + 13 - (e - 127));
-                    inv_scale = pow2_biased(127 - 13 + (e - 127)) * inv_w_scale;
-                    const f2 s2 = pk(s, s);
-                    if (!(a.debug & 8)) {
-                    uint32_t hi_h[16], lo_h[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const f2 sc = mul2(pk(z[2 * j], z[2 * j + 1]), s2);
-                        float s0, s1, h0, h1, l0, l1;
-                        upk(sc, s0, s1);
-                        hi_h[j] = pack_h2(s0, s1);
-                        unpack_h2(hi_h[j], h0, h1);
-                        upk(sub2(sc, pk(h0, h1)), l0, l1);
-                        lo_h[j] = pack_h2(l0, l1);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        *reinterpret_cast<uint4*>(a_tile + r * 128 + ((c ^ (r & 7)) << 4)) =
-                            make_uint4(hi_h[4 * c], hi_h[4 * c + 1], hi_h[4 * c + 2], hi_h[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(a_tile + r * 128 + (((c + 4) ^ (r & 7)) << 4)) =
-                            make_uint4(lo_h[4 * c], lo_h[4 * c + 1], lo_h[4 * c + 2], lo_h[4 * c + 3]);
-                    }
-                    const float sb = s * beta;            // <= 2^13 by construction; exact, flushes to 0 far below the row maximum
-                    *reinterpret_cast<uint32_t*>(a_aug + aug_off(r, 0)) = pack_h2(sb, sb);
-                    }
+                } else if (!(a.debug & 8)) {
+                    inv_scale = split_store_fp16(z, a_tile, a_aug, r, beta, inv_w_scale);
                 }
                 if (!(a.debug & 2)) fence_proxy_async_smem();
                 tc_fence_before();
@@ -348,7 +297,7 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 
             float y[kH], k1[kH], s23[kH];
             {
-                const float4* zp = reinterpret_cast<const float4*>(a.z0 + lpath * kH);
+                const float4* zp = reinterpret_cast<const float4*>((seg == 0 ? a.z0 : un.ystate) + lpath * kH);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     const float4 v = zp[c4];
@@ -357,31 +306,29 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 #pragma unroll
                 for (int h = 0; h < kH; ++h) { k1[h] = 0.f; s23[h] = 0.f; }
             }
-            int jn = 0;
-            int next_out = (a.n_out > 0) ? a.out_step[0] : 0x7fffffff;
-            while (jn < a.n_out && next_out < 0) {
+            int jn = (seg == 0) ? 0 : un.seg_first_out[seg];
+            int next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
+            while (seg == 0 && jn < a.n_out && next_out < 0) {         // outputs at the initial time
                 write_out(jn, y);
                 ++jn;
                 next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
             }
-            write_a(y, 0);
-            if (issuer_warp) issue_stage(0);
+            write_a(y, st_lo);
 
             const float third = (float)(1.0 / 3.0);
-            int step = 0, sub = 0;
-            float dt = a.step_dt[0];
-            float dt_next = (a.n_steps > 1) ? a.step_dt[1] : 0.f;
-            float frac0 = a.stage_frac[0];                        // this stage's fraction
-            float frac1 = (total > 1) ? a.stage_frac[1] : 0.f;    // next stage's, read a full stage ahead
-            uint32_t phase = 0;
-            for (int st = 0; st < total; ++st) {
-                const bool more = st + 1 < total;
-                // ---- in the MMA's shadow: dX/dt from the prefetched row (interpolation_cubic.py:331-336), times the
-                //      sign of the time direction and (MODE 1) the inverse of the operand scales
-                if (!(a.debug & 1)) mbar_wait(&raw_full[2 * t + (st & 1)], (uint32_t)((st >> 1) & 1));
+            int step = step_lo, sub = 0;
+            float dt = a.step_dt[step_lo];
+            float dt_next = (step_lo + 1 < a.n_steps) ? a.step_dt[step_lo + 1] : 0.f;
+            float frac0 = a.stage_frac[st_lo];                            // this stage's fraction
+            float frac1 = (st_lo + 1 < st_hi) ? a.stage_frac[st_lo + 1] : 0.f;   // next stage's, read a full stage ahead
+            for (int st = st_lo; st < st_hi; ++st) {
+                const bool more = st + 1 < st_hi;
+                // ---- in the MMA's shadow: dX/dt from the rows the TMA unit delivered (interpolation_cubic.py:331-336),
+                //      times the sign of the time direction and (MODE 1) the inverse of the operand scales
+                if (!(a.debug & 1)) mbar_wait(&raw_full[2 * t + (kcount & 1)], (kcount >> 1) & 1);
                 f2 dx2[kC / 2];
                 {
-                    const unsigned char* rows = raw_tile + (st & 1) * S::raw_buf;
+                    const unsigned char* rows = raw_tile + (kcount & 1) * S::raw_buf;
                     if (cubic) {
                         // row r of the TMA box = [a | b | 2c | 3d], 16-byte chunk c at position c ^ (r & 7)
                         const unsigned char* row = rows + r * 128;
@@ -403,42 +350,24 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 #pragma unroll
                     for (int q = 0; q < 4; ++q) dx2[q] = mul2(dx2[q], p2);
                 }
+                ++kcount;
                 frac0 = frac1;
-                if (st + 2 < total) frac1 = a.stage_frac[st + 2];
+                if (st + 2 < st_hi) frac1 = a.stage_frac[st + 2];
 
-                const bool tr = TRACE && a.trace && blockIdx.x == 0 && t == 0 && r == 0 && st < 64;
+                const bool tr = TRACE && a.trace && u == 0 && t == 0 && r == 0 && st < 64;
                 if (tr) a.trace[st * 8 + 2] = clock64();
-                mbar_wait(&d_ready[t], phase);
-                phase ^= 1;
+                mbar_wait(&d_ready[t], phase_d);
+                phase_d ^= 1;
                 tc_fence_after();
                 if (tr) a.trace[st * 8 + 3] = clock64();
 
-                // ---- kv[h] = sum_c D[h*C + c] * dX[c]  (the bias is already in D); packed FFMA2, next TMEM
-                //      load in flight while the current 16 columns are consumed
+                // ---- kv[h] = sum_c D[h*C + c] * dX[c]  (the bias is already in D); packed FFMA2
                 float kv[kH];
                 if (a.debug & 4) {
 #pragma unroll
                     for (int h = 0; h < kH; ++h) kv[h] = y[h] * 1e-3f;
                 } else {
-                    // 32-column loads, the next one in flight while the current one is consumed (see umma.cuh)
-                    uint32_t va[32], vb[32];
-                    tmem_ld32_issue(taddr, va);
-#pragma unroll
-                    for (int j = 0; j < kN / 32; ++j) {
-                        uint32_t* cur = (j & 1) ? vb : va;
-                        tmem_ld32_wait(cur);
-                        if (j + 1 < kN / 32) tmem_ld32_issue(taddr + (uint32_t)(32 * (j + 1)), (j & 1) ? va : vb);
-#pragma unroll
-                        for (int hh = 0; hh < 4; ++hh) {
-                            f2 acc = mul2(pk(__uint_as_float(cur[8 * hh + 0]), __uint_as_float(cur[8 * hh + 1])), dx2[0]);
-                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 2]), __uint_as_float(cur[8 * hh + 3])), dx2[1], acc);
-                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 4]), __uint_as_float(cur[8 * hh + 5])), dx2[2], acc);
-                            acc = fma2(pk(__uint_as_float(cur[8 * hh + 6]), __uint_as_float(cur[8 * hh + 7])), dx2[3], acc);
-                            float lo, hi;
-                            upk(acc, lo, hi);
-                            kv[4 * j + hh] = lo + hi;
-                        }
-                    }
+                    contract_row<TCDE_TC_LD_WIDTH>(taddr, dx2, kv);
                 }
 
                 if (tr) a.trace[st * 8 + 4] = clock64();
@@ -493,10 +422,7 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                     step_done = true;
                 }
                 if (tr) a.trace[st * 8 + 5] = clock64();
-                if (more) {                               // hand the next stage to the tensor core first ...
-                    write_a(kv, st + 1);
-                    if (issuer_warp) issue_stage(st + 1);
-                }
+                if (more) write_a(kv, st + 1);            // hand the next stage to the tensor core first ...
                 if (tr) a.trace[st * 8 + 6] = clock64();
                 if (step_done) {                          // ... then the bookkeeping that nobody waits for
                     while (next_out == step) {
@@ -523,8 +449,18 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
                     ++sub;
                 }
             }
+            if (seg + 1 < un.n_seg && live) {             // hand the state over to whoever runs the next segment
+                float4* dst = reinterpret_cast<float4*>(un.ystate + path * kH);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
+                __threadfence();
+            }
+            }
+            TCDE_UNIT_EPILOGUE()
         }
     }
+#undef TCDE_UNIT_PROLOGUE
+#undef TCDE_UNIT_EPILOGUE
     tc_fence_before();
     __syncthreads();
     if (warp == kAllocWarp) tmem_dealloc(tmem_base, 512);
@@ -532,12 +468,31 @@ __global__ void __launch_bounds__(kRowThreads + (ISSUER ? kIssuerThreads : 0), 1
 
 }  // namespace tc
 
-template <int MODE, bool ISSUER> static int launch_tc(const UmmaArgs& a, cudaStream_t stream) {
-    const int64_t per_cta = tc::kTile * tc::kTiles;
-    const int64_t ctas = (a.n_paths + per_cta - 1) / per_cta;
-    TCDE_CHECK_SUPPORTED(ctas < (1ll << 31), "too many paths");
-    auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, ISSUER, false, true>
-                             : a.trace ? tc::cdeint_tc_kernel<MODE, ISSUER, true, false> : tc::cdeint_tc_kernel<MODE, ISSUER, false, false>;
+// n_seg: the smallest power of two (<= 8, segments of >= 8 steps) that minimises ceil(units / SMs) / n_seg
+static int choose_segments(int64_t n_pairs, int n_steps, int sms) {
+    int best = 1;
+    double best_cost = (double)((n_pairs + sms - 1) / sms);
+    for (int s = 2; s <= 8; s *= 2) {
+        if (n_steps / s < 8) break;
+        const int64_t units = n_pairs * s;
+        const double cost = (double)((units + sms - 1) / sms) / s;
+        if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+template <int MODE> static int launch_tc(const UmmaArgs& a, cudaStream_t stream) {
+    const int64_t n_pairs = (a.n_paths + tc::kRowThreads - 1) / tc::kRowThreads;
+    TCDE_CHECK_SUPPORTED(n_pairs < (1ll << 28), "too many paths");
+    const int sms = sm_count();
+    // debug bit 4 (16): never cut the time axis; bit 5 (32): always cut it in (up to) four segments -- the tests use it to
+    // exercise the hand-over on small batches
+    const int n_seg = (a.debug & 16) ? 1 : (a.debug & 32) ? (a.n_steps >= 4 ? 4 : a.n_steps) : choose_segments(n_pairs, a.n_steps, sms);
+    const int steps_per_seg = (a.n_steps + n_seg - 1) / n_seg;
+    const int64_t n_units = n_pairs * n_seg;
+    const int grid = (int)(n_units < sms ? n_units : sms);
+    auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, false, true>
+                             : a.trace ? tc::cdeint_tc_kernel<MODE, true, false> : tc::cdeint_tc_kernel<MODE, false, false>;
     constexpr int smem = tc::Smem<MODE>::total + 1024;      // slack for the 1024-byte alignment of the tiles
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     alignas(64) CUtensorMap rows_map;
@@ -545,8 +500,27 @@ template <int MODE, bool ISSUER> static int launch_tc(const UmmaArgs& a, cudaStr
     const int rc = tc::make_rows_tensor_map(&rows_map, a.control, a.n_paths, a.n_rows, row_floats);
     TCDE_CHECK_SUPPORTED(rc == 0, "tensor-core solve: cuTensorMapEncodeTiled failed (%d) for control [%lld][%lld x %d floats]", rc,
                          (long long)a.n_paths, (long long)a.n_rows, row_floats);
-    kern<<<(unsigned)ctas, tc::kRowThreads + (ISSUER ? tc::kIssuerThreads : 0), smem, stream>>>(a, rows_map);
-    TCDE_CHECK_CUDA(cudaGetLastError());
+
+    tc::Units un{n_seg, steps_per_seg, nullptr, nullptr, nullptr};
+    void* workspace = nullptr;
+    if (n_seg > 1) {
+        // hand-over state + flags + the per-segment output cursor: stream-ordered scratch, freed right after the launch
+        // (nothing outlives the call; the caller's buffers stay the only persistent memory, as the C ABI promises)
+        const size_t y_bytes = (size_t)a.n_paths * tc::kH * sizeof(float);
+        const size_t flag_bytes = ((size_t)n_pairs * sizeof(int) + 255) & ~(size_t)255;
+        const size_t cur_bytes = ((size_t)n_seg * sizeof(int32_t) + 255) & ~(size_t)255;
+        TCDE_CHECK_CUDA(cudaMallocAsync(&workspace, y_bytes + flag_bytes + cur_bytes, stream));
+        un.ystate = static_cast<float*>(workspace);
+        un.progress = reinterpret_cast<int*>(static_cast<char*>(workspace) + y_bytes);
+        int32_t* cursor = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + y_bytes + flag_bytes);
+        un.seg_first_out = cursor;
+        TCDE_CHECK_CUDA(cudaMemsetAsync(un.progress, 0, flag_bytes, stream));
+        tc::segment_cursor_kernel<<<1, 32, 0, stream>>>(a.out_step, a.n_out, n_seg, steps_per_seg, cursor);
+    }
+    kern<<<grid, tc::kThreads, smem, stream>>>(a, un, rows_map);
+    const cudaError_t launch_err = cudaGetLastError();
+    if (workspace) cudaFreeAsync(workspace, stream);
+    TCDE_CHECK_CUDA(launch_err);
     return TCDE_OK;
 }
 
@@ -557,13 +531,8 @@ int solve_tc_f32(const UmmaArgs& a, int H, int C, int mode, cudaStream_t stream)
                          "tensor-core solve: control, z0 and out must be 16-byte aligned");
     TCDE_CHECK_SUPPORTED(a.stage_dump == nullptr || (reinterpret_cast<uintptr_t>(a.stage_dump) & 15) == 0,
                          "tensor-core solve: the stage dump must be 16-byte aligned");
-    // mode: bit 0 = operand split (0 = 3xTF32, 1 = 2xFP16), bit 1 = dedicated issuer warpgroup
-    switch (mode & 3) {
-        case 0: return launch_tc<0, false>(a, stream);
-        case 1: return launch_tc<1, false>(a, stream);
-        case 2: return launch_tc<0, true>(a, stream);
-        default: return launch_tc<1, true>(a, stream);
-    }
+    // mode: bit 0 = operand split (0 = 3xTF32, 1 = 2xFP16)
+    return (mode & 1) ? launch_tc<1>(a, stream) : launch_tc<0>(a, stream);
 }
 
 }  // namespace tcde

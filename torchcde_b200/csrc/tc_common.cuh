@@ -127,9 +127,10 @@ __device__ __forceinline__ void prepare_b_fp16(unsigned char* b_tile, unsigned c
 // row) plus the row's entry of the bias block.  Returns 1 / (row scale * weight scale), to be folded into dX/dt.
 __device__ __forceinline__ float split_store_fp16(const float* z, unsigned char* a_tile, unsigned char* a_aug, int r, float beta,
                                                   float inv_w_scale) {
-    float m = beta;
+    float mx[8];                          // a tree, not a 32-long dependent chain
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) m = fmaxf(m, fabsf(z[k]));
+    for (int k = 0; k < 8; ++k) mx[k] = fmaxf(fmaxf(fabsf(z[k]), fabsf(z[k + 8])), fmaxf(fabsf(z[k + 16]), fabsf(z[k + 24])));
+    const float m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), beta));
     const int e = min(max(exponent_of(m), 30), 224);
     const float s = pow2_biased(127 + 13 - (e - 127));
     const f2 s2 = pk(s, s);
@@ -173,26 +174,41 @@ __device__ __forceinline__ void issue_fp16(uint32_t tmem_d, const unsigned char*
     mma_commit(d_ready);
 }
 
-// kv[h] = sum_c D[h * 8 + c] * dx[c] for the thread's own accumulator row (256 TMEM columns from taddr)
+// kv[h] = sum_c D[h * 8 + c] * dx[c] for the thread's own accumulator row (256 TMEM columns from taddr); W = columns per
+// TMEM load (16 or 32), the next load in flight while the current one is consumed (see umma.cuh)
+template <int W>
 __device__ __forceinline__ void contract_row(uint32_t taddr, const f2* dx2, float* kv) {
-    uint32_t va[16], vb[16];
-    tmem_ld16_issue(taddr, va);
+    uint32_t va[W], vb[W];
+    if (W == 32) tmem_ld32_issue(taddr, va); else tmem_ld16_issue(taddr, va);
 #pragma unroll
-    for (int j = 0; j < kCols / 16; ++j) {
+    for (int j = 0; j < kCols / W; ++j) {
         uint32_t* cur = (j & 1) ? vb : va;
-        tmem_ld16_wait(cur);
-        if (j + 1 < kCols / 16) tmem_ld16_issue(taddr + (uint32_t)(16 * (j + 1)), (j & 1) ? va : vb);
+        if (W == 32) tmem_ld32_wait(cur); else tmem_ld16_wait(cur);
+        if (j + 1 < kCols / W) {
+            if (W == 32) tmem_ld32_issue(taddr + (uint32_t)(W * (j + 1)), (j & 1) ? va : vb);
+            else tmem_ld16_issue(taddr + (uint32_t)(W * (j + 1)), (j & 1) ? va : vb);
+        }
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < W / 8; ++hh) {
             f2 acc = mul2(pk(__uint_as_float(cur[8 * hh + 0]), __uint_as_float(cur[8 * hh + 1])), dx2[0]);
             acc = fma2(pk(__uint_as_float(cur[8 * hh + 2]), __uint_as_float(cur[8 * hh + 3])), dx2[1], acc);
             acc = fma2(pk(__uint_as_float(cur[8 * hh + 4]), __uint_as_float(cur[8 * hh + 5])), dx2[2], acc);
             acc = fma2(pk(__uint_as_float(cur[8 * hh + 6]), __uint_as_float(cur[8 * hh + 7])), dx2[3], acc);
             float lo, hi;
             upk(acc, lo, hi);
-            kv[2 * j + hh] = lo + hi;
+            kv[(W / 8) * j + hh] = lo + hi;
         }
     }
+}
+
+// seg_first_out[s] = number of requested outputs that fall before segment s's first step (host schedule: out_step[j] is the
+// step in which output j is produced, -1 for outputs at the initial time); one tiny launch per solve that is cut in segments
+static __global__ void segment_cursor_kernel(const int32_t* out_step, int n_out, int n_seg, int steps_per_seg, int32_t* cursor) {
+    const int s = threadIdx.x;
+    if (s >= n_seg) return;
+    int j = 0;
+    while (j < n_out && out_step[j] < s * steps_per_seg) ++j;
+    cursor[s] = j;
 }
 
 }  // namespace tc
