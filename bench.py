@@ -446,6 +446,40 @@ def run_gpu_arm(args):
                             "(tcde_cdeint_fixed_linear_stages x2, tcde_linear_field_param_grads); not the headline"}
             except Exception as exc:      # never lose the headline line over the extra
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {"error": repr(exc)}
+            # BASELINE config 4: the reference's default call (dopri5, adjoint=True) at the same shapes
+            config4 = {}
+            try:
+                def fwd4():
+                    holder["c4"] = cde.cdeint(X, func, z0, t, adjoint=True)          # no grad needed: forward only
+
+                f_ms = time_loop(fwd4, 2, 1, device) / 2
+                st4 = dict(cde.cdeint.last_stats)
+                config4 = {"workload": "cdeint(X, func, z0, X.interval) -- torchdiffeq defaults: dopri5, rtol 1e-4, atol 1e-6, "
+                                       "adjoint=True -- batch 65536, len 256, ch 8, hid 32",
+                           "forward": {"ms": f_ms, "sequences_per_s": BATCH / (f_ms * 1e-3), "accepted_steps": st4.get("n_accepted"),
+                                       "rejected_steps": st4.get("n_rejected"), "launches": st4.get("launches"),
+                                       "device_controlled": st4.get("device_controlled"),
+                                       "kernel": "dopri5_attempt_kernel: one launch per attempted step, controller and dense "
+                                                 "output on the device, one host read per 48 launches"}}
+
+                def train4():
+                    zz = z0.clone().requires_grad_(True)
+                    func.zero_grad()
+                    with torch.enable_grad():
+                        res = cde.cdeint(X, func, zz, t, adjoint=True)
+                        res[:, -1].sum().backward()
+
+                t0 = time.perf_counter()
+                train4()
+                torch.cuda.synchronize(device)
+                b_s = time.perf_counter() - t0
+                config4["forward_plus_adjoint_backward"] = {
+                    "ms": b_s * 1e3, "sequences_per_s": BATCH / b_s, "runs": 1,
+                    "note": "backward = this package's continuous adjoint with dopri5 on the augmented state, one fused "
+                            "field+vjp launch per evaluation, host-driven controller (one read per attempt)"}
+            except Exception as exc:
+                config4["error"] = repr(exc)
+            extra["config4_dopri5_adjoint"] = config4
 
     if rank != 0:
         if dist is not None:
@@ -460,9 +494,17 @@ def run_gpu_arm(args):
     achieved_tf = BATCH * FLOPS_PER_SEQ / kernel_s / 1e12
     fp32_peak_tf = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
-    variant = args.variant if args.variant is not None else 0
-    tensor_kernel = variant in (0, 2)
-    mma_flops = BATCH * 255 * 4 * 3 * 2 * HIDDEN * HIDDEN * CHANNELS      # 3xTF32: three MMAs per product
+    variant = (args.variant if args.variant is not None else 0) & 15
+    tensor_kernel = variant != 1
+    fp16_split = variant in (0, 4, 5)
+    mmas_per_stage = 7 if fp16_split else 13        # 128 x 256 x (16 halves | 8 tf32) each: the same 2 * 128 * 256 * 16 / 2 ... flops per cycle-slot
+    mma_flops = BATCH / 128 * 255 * 4 * mmas_per_stage * 2 * 128 * 256 * (16 if fp16_split else 8)
+    mma_peak = peaks["bf16_tflops"] if fp16_split else peaks["bf16_tflops"] / 2
+    kernel_name = {0: "cdeint_tc_kernel<1> (tcgen05.mma kind::f16, 2xFP16 split, TMA rows, persistent)", 2: "cdeint_umma_kernel<8> (round 1, 3xTF32)",
+                   3: "cdeint_tc_kernel<0> (3xTF32)", 4: "cdeint_tc_kernel<1> (2xFP16)", 5: "cdeint_tc_kernel<1> (2xFP16)",
+                   6: "cdeint_tc_kernel<0> (3xTF32)"}.get(variant, "?")
+    secondary = dict(extra)
+    config4 = secondary.get("config4_dopri5_adjoint")
     line = {
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -481,26 +523,31 @@ def run_gpu_arm(args):
         "gpu_launches": args.steps,
         "roofline": ({
             "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2166000000, "peak_source": peaks["source"],
-            "kernel": "cdeint_umma_kernel<8> (tcgen05.mma kind::tf32, 3xTF32 split)",
+            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2165000000, "peak_source": peaks["source"],
+            "kernel": kernel_name,
             "algorithmic_flops_per_launch": BATCH * FLOPS_PER_SEQ,
             "note": "achieved = ALGORITHMIC flops (17.6 MFLOP/seq) / time against the measured dense bf16 peak, as the "
-                    "contract asks. The kernel runs kind::tf32 (half the bf16 rate) and needs 3 MMAs per product for "
-                    "fp32 accuracy, so its own ceiling is peak/6; see tf32 below. traffic = dram bytes of one launch "
-                    "from the ncu capture in profiles/ (algorithmic bytes: 1.63e9).",
-            "tf32": {"executed_mma_tflops": mma_flops / kernel_s / 1e12, "peak_tflops": peaks["bf16_tflops"] / 2,
-                     "frac": mma_flops / kernel_s / 1e12 / (peaks["bf16_tflops"] / 2),
-                     "peak_source": "measured dense bf16 / 2 (tf32 runs at half the bf16 rate)"},
+                    "contract asks. fp32 accuracy on the tensor pipe costs a 2-way operand split: 3 partial products + 1 bias "
+                    "block = 7 FP16 MMAs (13 TF32 MMAs in round 1) per 128 x 256 x 32 product, so the kernel's own ceiling is "
+                    "peak * 2 / 7; see mma below (executed MMA flops against the same peak). The pace is set by the serial "
+                    "chain MMA -> TMEM read -> Runge-Kutta -> operand split of the two tiles TMEM can hold, not by the pipe "
+                    "(profiles/README.md). traffic = dram bytes of one launch from the ncu capture in profiles/ "
+                    "(algorithmic bytes: 1.63e9; whole 128-byte coefficient rows are fetched).",
+            "mma": {"executed_mma_tflops": mma_flops / kernel_s / 1e12, "peak_tflops": mma_peak,
+                    "frac": mma_flops / kernel_s / 1e12 / mma_peak, "mmas_per_tile_stage": mmas_per_stage,
+                    "peak_source": "measured dense bf16 (kind::f16 rate)" if fp16_split else "measured dense bf16 / 2 (tf32 rate)"},
             "hbm": {"achieved_gbs": achieved_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": achieved_gbs / peaks["hbm_gbs"],
                     "note": "the north_star's HBM framing: this solve is ~700 flop/B, compute bound by ~60x"},
+            "secondary": secondary,
         } if tensor_kernel else {
             "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": 2176804000, "peak_source": peaks["source"],
             "kernel": "cdeint_simt_kernel<float,8,8>", "algorithmic_bytes_per_launch": BATCH * BYTES_PER_SEQ,
             "note": "this kernel is FP32-FMA bound (708 flop/B), not HBM bound; see fp32 below and DESIGN.md",
             "fp32": {"achieved_tflops": achieved_tf, "peak_tflops": fp32_peak_tf, "frac": achieved_tf / fp32_peak_tf,
-                     "peak_source": "148 SMs x 128 FMA lanes x 2 x clocks.max.sm"}}),
-        "kernels": extra,
+                     "peak_source": "148 SMs x 128 FMA lanes x 2 x clocks.max.sm"},
+            "secondary": secondary}),
+        "config4": config4,
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline()

@@ -575,7 +575,7 @@ static int solve_fixed_linear(const void* control, int control_kind, int64_t n_r
                        (const float*)step_dt, stage_index, (const float*)stage_frac, out_step, out_mode,
                        (const float*)out_slope, n_paths, n_rows, control_kind, method, n_stages, (int)n_steps,
                        (int)n_out, (float)sign, g_trace, (float*)stage_dump, g_debug_flags};
-            if (g_solve_variant == 2 || g_solve_variant == 0) return solve_umma_f32(u, (int)hidden, (int)channels, s);   // TODO r2: auto -> solve_tc once validated on the GPU
+            if (g_solve_variant == 2) return solve_umma_f32(u, (int)hidden, (int)channels, s);        // the round-1 kernel, kept for comparison
             // round-2 kernel: 3 / 6 = 3xTF32 split, 4 / 5 = 2xFP16 split (5, 6: aliases from the development history)
             const int mode = (g_solve_variant == 3 || g_solve_variant == 6) ? 0 : (g_solve_variant == 4 || g_solve_variant == 5) ? 1
                                                                                                                                   : TCDE_DEFAULT_TC_MODE;

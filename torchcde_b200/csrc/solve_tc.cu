@@ -297,10 +297,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
 
             float y[kH], k1[kH], s23[kH];
             {
+                // the hand-over state was written by another SM during this launch: read it through L2 (ld.global.cg), never
+                // from this SM's L1, which may still hold the line from an earlier segment of the same paths
                 const float4* zp = reinterpret_cast<const float4*>((seg == 0 ? a.z0 : un.ystate) + lpath * kH);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 v = zp[c4];
+                    const float4 v = (seg == 0) ? zp[c4] : __ldcg(zp + c4);
                     y[4 * c4] = v.x; y[4 * c4 + 1] = v.y; y[4 * c4 + 2] = v.z; y[4 * c4 + 3] = v.w;
                 }
 #pragma unroll
@@ -313,6 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                 ++jn;
                 next_out = (jn < a.n_out) ? a.out_step[jn] : 0x7fffffff;
             }
+            // the two tiles of a CTA share one tensor pipe: started together they stay in lockstep and each waits for the
+            // other's 7 MMAs every stage (measured: 1,990 cycles from issue to d_ready instead of ~1,150); half a stage of
+            // head start for tile 0, once per unit, keeps them in anti-phase
+            if (t == 1 && !(a.debug & 64)) __nanosleep(800);
             write_a(y, st_lo);
 
             const float third = (float)(1.0 / 3.0);
