@@ -107,22 +107,14 @@ def test_dopri5_jump_t_on_linear_control():
     x, z0, func = _problem(16, 12, 8, 32, seed=6)
     func = func.to(DEV)
     counts = []
-    real = adaptive.Dopri5.integrate
-
-    def counting(self, times):
-        out = real(self, times)
-        counts.append((self.n_accepted, self.n_rejected))
-        return out
-
-    adaptive.Dopri5.integrate = counting
-    try:
-        with torch.no_grad():
-            X = cde.LinearInterpolation(x.to(DEV))
-            plain = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8)
-            jumped = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8,
-                                options=dict(jump_t=X.grid_points))
-    finally:
-        adaptive.Dopri5.integrate = real
+    with torch.no_grad():
+        X = cde.LinearInterpolation(x.to(DEV))
+        plain = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8)
+        counts.append((cde.cdeint.last_stats["n_accepted"], cde.cdeint.last_stats["n_rejected"]))     # device-controlled driver
+        jumped = cde.cdeint(X, func, z0.to(DEV), X.interval, adjoint=False, rtol=1e-6, atol=1e-8,
+                            options=dict(jump_t=X.grid_points))
+        counts.append((cde.cdeint.last_stats["n_accepted"], cde.cdeint.last_stats["n_rejected"]))     # host driver (jump_t)
+        assert not cde.cdeint.last_stats["device_controlled"]
     want = _exact_piecewise_linear(x.double(), func.linear.weight.detach().cpu().double(),
                                    func.linear.bias.detach().cpu().double(), z0.double(), 11)
     scale = float(want.abs().max())
