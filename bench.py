@@ -446,6 +446,35 @@ def run_gpu_arm(args):
                             "(tcde_cdeint_fixed_linear_stages x2, tcde_linear_field_param_grads); not the headline"}
             except Exception as exc:      # never lose the headline line over the extra
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {"error": repr(exc)}
+            # a generic (non-linear) func through this package's stage loop -- the MLP + tanh field of
+            # example/time_series_classification.py:37-51 (hidden 8, 3 input channels), batch 65536, length 256, rk4 step 1
+            try:
+                class MlpField(torch.nn.Module):
+                    def __init__(self):
+                        super().__init__()
+                        self.linear1 = torch.nn.Linear(8, 128)
+                        self.linear2 = torch.nn.Linear(128, 24)
+
+                    def forward(self, tt, z):
+                        z = self.linear2(self.linear1(z).relu()).tanh()
+                        return z.view(*z.shape[:-1], 8, 3)
+
+                torch.manual_seed(2)
+                mlp = MlpField().to(device)
+                Xg = cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x[..., :3].contiguous()))
+                zg = z0[:, :8].contiguous()
+                g_rows = {}
+                for label, opts in (("kernel_loop", {"step_size": 1.0}), ("cuda_graph", {"step_size": 1.0, "cuda_graph": True})):
+                    fn = lambda: cde.cdeint(Xg, mlp, zg, t, adjoint=False, method="rk4", options=opts)  # noqa: E731
+                    g_ms = time_loop(fn, 2, 1, device) / 2
+                    g_rows[label] = {"ms": g_ms, "sequences_per_s": BATCH / (g_ms * 1e-3)}
+                extra["generic_mlp_field_rk4"] = dict(g_rows, note="func = Linear(8,128)-ReLU-Linear(128,24)-tanh (the reference example's "
+                                                     "field), CubicSpline control with 3 channels; 12 launches per stage: dX/dt of a "
+                                                     "step in one tcde_spline_eval launch, every Runge-Kutta combination one "
+                                                     "tcde_linear_combination launch; func itself stays torch operators")
+                del Xg, zg
+            except Exception as exc:
+                extra["generic_mlp_field_rk4"] = {"error": repr(exc)}
             # BASELINE config 4: the reference's default call (dopri5, adjoint=True) at the same shapes
             config4 = {}
             try:

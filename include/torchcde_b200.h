@@ -229,6 +229,16 @@ TCDE_API int tcde_dopri5_linear_attempts(const void* control, int control_kind, 
                                 const void* out_times, int64_t n_out, int64_t n_paths, int64_t channels, int64_t hidden,
                                 double sign, int64_t first_seq, int64_t n_launches, int dtype, void* stream);
 
+/* Logsignatures of windows of piecewise-linear paths -- replaces the per-window call of the optional third-party package
+ * at torchcde/log_ode.py:56-58 (``signatory.Logsignature(depth)``, default "words" basis).  x [n_paths][length][channels]
+ * (NaN free); window w spans the points window_index[w] .. window_index[w + 1] (device int32 [n_windows + 1]); words: device
+ * int32 [n_words][2] = (level, flat index i_1 * C^(k-1) + ... + i_k) of the Lyndon words; out [n_paths][n_windows][n_words].
+ * channels^1 + ... + channels^depth must not exceed tcde_logsignature_max_terms(). */
+TCDE_API int64_t tcde_logsignature_max_terms(void);
+TCDE_API int tcde_logsignature_windows(const void* x, int64_t n_paths, int64_t length, int64_t channels,
+                              const int32_t* window_index, int64_t n_windows, int depth, const int32_t* words, int64_t n_words,
+                              void* out, int dtype, void* stream);
+
 /* Profiling aid: a device buffer of 64 x 8 int64 that the tensor-core solve kernel (variant 2)
  * fills with clock64 stamps of CTA 0 / tile 0 for its first 64 stages; NULL (default) disables. */
 TCDE_API int tcde_set_trace_buffer(void* device_buffer);

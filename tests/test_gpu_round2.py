@@ -114,3 +114,42 @@ def test_linear_interpolation_state_dict_matches_the_reference_keys():
     # a module built on the CPU and moved afterwards carries the same slopes
     Xc = cde.LinearInterpolation(a.cpu()).to(DEV)
     assert torch.equal(Xc._derivs, want)
+
+
+class _MlpField(torch.nn.Module):
+    """The vector field of example/time_series_classification.py:37-51 (MLP + tanh)."""
+
+    def __init__(self, input_channels, hidden_channels):
+        super().__init__()
+        self.input_channels, self.hidden_channels = input_channels, hidden_channels
+        self.linear1 = torch.nn.Linear(hidden_channels, 128)
+        self.linear2 = torch.nn.Linear(128, input_channels * hidden_channels)
+
+    def forward(self, t, z):
+        z = self.linear2(self.linear1(z).relu()).tanh()
+        return z.view(*z.shape[:-1], self.hidden_channels, self.input_channels)
+
+
+@pytest.mark.parametrize("method,step", [("rk4", 1.0), ("midpoint", 0.5), ("euler", 0.25)])
+def test_generic_field_kernel_loop_and_cuda_graph(method, step):
+    """an arbitrary func runs through this package's stage loop -- dX/dt of a step's stages in one launch,
+    Runge-Kutta combinations as single launches, optionally the whole loop as one CUDA graph -- with the numbers of the
+    differentiable torch-operator loop (which is what autograd uses)."""
+    from torchcde_b200 import solver
+    torch.manual_seed(0)
+    x = torch.randn(64, 20, 3, device=DEV).cumsum(1) / 4
+    func = _MlpField(3, 8).to(DEV)
+    z0 = torch.randn(64, 8, device=DEV)
+    t = torch.tensor([0.0, 7.3, 19.0])
+    for make in (lambda: cde.CubicSpline(cde.natural_cubic_coeffs(x)), lambda: cde.LinearInterpolation(x)):
+        X = make()
+        with torch.no_grad():
+            fast = cde.cdeint(X, func, z0, t, adjoint=False, method=method, options={"step_size": step})
+            graph = cde.cdeint(X, func, z0, t, adjoint=False, method=method, options={"step_size": step, "cuda_graph": True})
+            again = cde.cdeint(X, func, z0 * 0.5, t, adjoint=False, method=method, options={"step_size": step, "cuda_graph": True})
+            half = cde.cdeint(X, func, z0 * 0.5, t, adjoint=False, method=method, options={"step_size": step})
+            slow = solver._generic_solve(X, func, z0, t, method, step, False, True)
+        assert fast.shape == (64, 3, 8)
+        assert torch.allclose(fast, slow, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(graph, fast, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(again, half, rtol=1e-6, atol=1e-6)          # the replay really read the new z0

@@ -306,6 +306,94 @@ def _generic_solve(X, func, z0, t, method, step_size, is_prod, known_control):
     return torch.stack(outs, dim=-2)
 
 
+# ------------------------------------------------- generic func, no autograd: kernels + optional CUDA graph
+_graphs = {}
+
+
+def _generic_solve_kernels(X, func, z0, t, method, step_size, is_prod, use_graph=False):
+    """The fixed-step stage loop for an arbitrary ``func`` when nothing needs a gradient: the control's derivative of
+    the four stages of a step is ONE launch of ``tcde_spline_eval`` (the reference: ~10 small kernels and 4 host syncs
+    per stage, interpolation_cubic.py:315-336), every Runge-Kutta combination is ONE launch of
+    ``tcde_linear_combination``; only ``func`` itself and the ``f @ dX`` contraction stay torch operators (they are the
+    user's code).  With ``use_graph`` the whole time loop is captured into a CUDA graph once per (func, X, shapes,
+    schedule) and replayed -- for small states the loop is launch-bound (12 launches per stage), which is what a graph
+    removes.  The graph reads ``func``'s parameters and X's coefficients from their own storage, so in-place updates of
+    either are seen by a replay; a different ``func`` / ``X`` object captures anew."""
+    kind, _, channels, n_rows = _control_signature(X)
+    dtype, device = z0.dtype, z0.device
+    sched = build_schedule(t, _schedule_knots(X), n_rows, method, step_size, dtype)
+    n_stages = sched.n_stages
+    control = (X._rows() if kind == _lib.CONTROL_CUBIC else X._coeffs).detach()
+    knots = X._t.detach().to(device=device, dtype=control.dtype).contiguous()
+    index_dev = sched.stage_index.to(device)
+    frac_dev = sched.stage_frac.to(device=device, dtype=control.dtype)
+    times_dev = sched.stage_times.to(device)
+    sign = sched.sign
+    from .controls import _eval_kernel
+    from .adaptive import _combine
+
+    def run(y0):
+        outs = [None] * sched.n_out
+        j = 0
+        while j < sched.n_out and int(sched.out_step[j]) < 0:
+            outs[j] = y0
+            j += 1
+        y = y0
+        for i in range(sched.n_steps):
+            # dX/dt of this step's stages: (..., n_stages, C) in one launch
+            dxs = _eval_kernel(control, knots, control.size(-2), channels, index_dev[i], frac_dev[i], kind, True)
+
+            def field(s, z):
+                ts = times_dev[i, s]
+                dx = dxs[..., s, :]
+                out = func.prod(ts, z, dx) if is_prod else (func(ts, z) @ dx.unsqueeze(-1)).squeeze(-1)
+                out = out if sign > 0 else -1.0 * out
+                return out if out.is_contiguous() else out.contiguous()
+
+            dt = float(sched.step_dt[i])
+            if method == "rk4":
+                k1 = field(0, y)
+                k2 = field(1, _combine(y, [k1], (1 / 3,), dt))
+                k3 = field(2, _combine(y, [k1, k2], (-1 / 3, 1.0), dt))
+                k4 = field(3, _combine(y, [k1, k2, k3], (1.0, -1.0, 1.0), dt))
+                y1 = _combine(y, [k1, k2, k3, k4], (0.125, 0.375, 0.375, 0.125), dt)
+            elif method == "midpoint":
+                k1 = field(0, y)
+                y1 = _combine(y, [field(1, _combine(y, [k1], (0.5,), dt))], (1.0,), dt)
+            else:
+                y1 = _combine(y, [field(0, y)], (1.0,), dt)
+            while j < sched.n_out and int(sched.out_step[j]) == i:
+                mode = int(sched.out_mode[j])
+                outs[j] = y if mode == 0 else y1 if mode == 1 else _combine(y, [y1, y], (1.0, -1.0), float(sched.out_slope[j]))
+                j += 1
+            y = y1
+        return torch.stack(outs, dim=-2)
+
+    zc = z0.detach().contiguous()
+    if not use_graph:
+        return run(zc)
+    key = (id(func), id(X), tuple(zc.shape), dtype, str(device), method, step_size, tuple(float(v) for v in t.detach().cpu().tolist()))
+    hit = _graphs.get(key)
+    if hit is None:
+        static_in = zc.clone()
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):                      # warm-up outside the capture (lazy initialisations)
+            run(static_in)
+        torch.cuda.current_stream(device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = run(static_in)
+        hit = (graph, static_in, static_out, func, X)      # func / X kept alive: their ids are the key
+        if len(_graphs) >= 8:
+            _graphs.clear()
+        _graphs[key] = hit
+    graph, static_in, static_out = hit[:3]
+    static_in.copy_(zc)
+    graph.replay()
+    return static_out.clone()
+
+
 # ------------------------------------------------------- fields for the host-driven drivers
 def _host_locator(X, state_dtype):
     """``(t_float, nudge) -> (interval index, fraction)`` with exactly the casts the reference stack
@@ -558,6 +646,8 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
             "torchcde_b200.cdeint: method={!r} is not built. Available: torchdiffeq's fixed-step {} and the adaptive "
             "'dopri5' (its default).".format(method, FIXED_METHODS))
     step_size = options.pop("step_size", None) if method in FIXED_METHODS else None
+    # this package's extension: capture the stage loop of a generic ``func`` in a CUDA graph (see _generic_solve_kernels)
+    use_graph = bool(options.pop("cuda_graph", False)) if method in FIXED_METHODS else False
     if method in FIXED_METHODS and options:
         raise NotImplementedError("torchcde_b200.cdeint: unsupported solver options {}".format(sorted(options)))
     if not isinstance(t, torch.Tensor):
@@ -652,6 +742,9 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
                     # a shape the fused kernels are not built for (e.g. hidden * channels * hidden beyond the
                     # shared-memory budget of the CUDA-core kernel): this package's own stage loop takes any shape
                     pass
+            if sig is not None and not torch.is_grad_enabled() and y0.is_cuda and y0.dtype in (torch.float32, torch.float64) \
+                    and sig[1] == tuple(y0.shape[:-1]):
+                return _generic_solve_kernels(X, func, y0, t, method, step_size, is_prod, use_graph).movedim(-2, 0)
             return _generic_solve(X, func, y0, t, method, step_size, is_prod, sig is not None).movedim(-2, 0)
         if (field_params is not None and adaptive.device_dopri5_available(y0, sig[2]) and not options.get("jump_t")
                 and set(options) <= {"first_step", "jump_t"}):
