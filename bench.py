@@ -439,9 +439,10 @@ def run_gpu_arm(args):
                         res = cde.cdeint(X, func, zz, t, adjoint=True, method="rk4", options=options)
                         res[:, -1].sum().backward()
 
-                t_ms = time_loop(train_step, 2, 1, device) / 2
+                train_step()                                          # allocates the two 8.6 GB stage trajectories once
+                t_ms = min(time_loop(train_step, 1, 0, device) for _ in range(3))
                 extra["cdeint_rk4_forward_plus_adjoint_backward"] = {
-                    "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "tensor (tf32); operand producers today",
+                    "ms": t_ms, "sequences_per_s": BATCH / (t_ms * 1e-3), "bound": "tensor (bf16 / f16 MMAs)", "runs": "best of 3",
                     "note": "backward = two tensor-core solves that keep their stage inputs + one tcgen05 GEMM for dL/dW, dL/db "
                             "(tcde_cdeint_fixed_linear_stages x2, tcde_linear_field_param_grads); not the headline"}
             except Exception as exc:      # never lose the headline line over the extra

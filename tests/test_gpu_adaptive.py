@@ -354,8 +354,10 @@ def test_trajectory_backward_matches_the_per_stage_backward(method, monkeypatch)
 @pytest.mark.parametrize("n_paths,n_stages", [(1, 1), (31, 3), (32, 2), (33, 5), (1000, 8), (4099, 40)])
 @pytest.mark.parametrize("kind", ["cubic", "linear"])
 def test_parameter_gradient_kernels_against_einsum(n_paths, n_stages, kind):
-    """tcde_linear_field_param_grads on the tensor cores (3xTF32, variant 0) and on the CUDA cores (variant 1) vs an
-    fp64 einsum over (stage, path): ragged path blocks, zero-weight stages, accumulation onto existing gradients."""
+    """tcde_linear_field_param_grads on the tensor cores (variant 0: round 2, BF16 two-way split, MN-major operands fed by
+    TMA; variant 2: round 1, 3xTF32) and on the CUDA cores (variant 1) vs an fp64 einsum over (stage, path): ragged path
+    blocks, zero-weight stages, accumulation onto existing gradients.  Bars: fp32-class (3e-5 of the largest entry) for the
+    TF32 / CUDA-core kernels, 2e-4 for the BF16 split (16 significant bits per operand: ample for a gradient)."""
     from torchcde_b200 import _lib
     gen = torch.Generator().manual_seed(n_paths + n_stages)
     hidden, channels, n_rows = 32, 8, 6
@@ -389,7 +391,7 @@ def test_parameter_gradient_kernels_against_einsum(n_paths, n_stages, kind):
     scale = -0.5
     index_d, frac_d, weight_d = index.to(DEV), frac.to(DEV), weight.to(DEV)     # kept alive across the launches
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             _lib.call("tcde_set_solve_variant", variant)
             gw0 = torch.randn(hidden * channels, hidden, generator=gen).to(DEV)
             gb0 = torch.randn(hidden * channels, generator=gen).to(DEV)
@@ -400,6 +402,7 @@ def test_parameter_gradient_kernels_against_einsum(n_paths, n_stages, kind):
                       _lib.ptr(scratch), n_paths, channels, hidden, scale, code, _lib.stream_of(z))
             torch.cuda.synchronize()
             for got, want in (((gw - gw0).double().cpu(), scale * want_w), ((gb - gb0).double().cpu(), scale * want_b)):
-                assert float((got - want).abs().max()) <= 3e-5 * max(1.0, float(want.abs().max())), variant
+                bar = 2e-4 if variant == 0 else 3e-5
+                assert float((got - want).abs().max()) <= bar * max(1.0, float(want.abs().max())), variant
     finally:
         _lib.call("tcde_set_solve_variant", 0)

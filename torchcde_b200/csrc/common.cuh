@@ -126,4 +126,11 @@ int param_grad_umma_f32(const float* control, int control_kind, int64_t n_rows, 
                         const float* stage_weight, int n_stage_total, float* scratch, int64_t n_paths, int grid,
                         cudaStream_t stream);
 
+// round 2: the same product with U on the N side (6 MMAs of N = 256 per 32 pairs instead of 24 of N = 48), BF16 two-way split,
+// MN-major operands, TMA-fed (param_grad_bf16.cu)
+int param_grad_bf16_grid(int64_t n_paths, int64_t n_stage_total);
+int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, const float* z_stages, const float* a_stages,
+                        const int32_t* stage_index, const float* stage_frac, const float* stage_weight, int n_stage_total,
+                        float* scratch, int64_t n_paths, int grid, cudaStream_t stream);
+
 }  // namespace tcde

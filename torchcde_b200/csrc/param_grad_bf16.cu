@@ -1,0 +1,295 @@
+// The parameter gradients of a whole fixed-step backward solve on the tensor cores, round 2 (sm_100a).
+//
+//   dL/dW[hC+c][k] = sum_e sum_p  w_e a_e[p][h] dX_e[p][c] * z_e[p][k]          (e: stages, p: paths)
+//   dL/db[hC+c]    = sum_e sum_p  w_e a_e[p][h] dX_e[p][c]
+//
+// is ONE matrix product over the (stage, path) pairs:  D[m][n] = sum_pairs Zx[pair][m] * U[pair][n]  with  Zx = (z | 1)
+// (33 of 128 rows used) and U = w a (x) dX formed on the fly (256 columns).  Round 1 (param_grad_umma.cu, kept as variant 1)
+// put U^T on the M side: 24 MMAs of N = 48 per 32 pairs -- at ~95 cycles of issue per tcgen05.mma whatever its size that is
+// 2,200 cycles per 32 pairs, 24 ms for the BASELINE backward; and every thread scattered 144 scalar shared-memory stores per
+// item (a transpose through shared memory).  Here:
+//   * U is the N side: ONE MMA covers all 256 columns -> 6 MMAs (M 128, N 256, K 16) per 32 pairs = 768 cycles of tensor pipe;
+//   * both operands are MN-major (the pair index is K): a thread's 8 products a[h] * dX[0..7] ARE one 16-byte chunk of its
+//     pair's row -- 128-bit stores straight into the canonical layout (8 k-rows x 128 B atoms, 128B swizzle), no transpose;
+//   * BF16 operands with a two-way split (hi + lo: z_lo.U_hi + z_hi.U_lo + z_hi.U_hi, error ~2^-16 per product -- a gradient
+//     needs no more, and unlike FP16 no scaling is needed: a per-pair scale cannot be factored out of a sum over pairs);
+//   * a, z and the spline rows of an item arrive by TMA (two 4 KB bulk copies + one tensor box of 32 paths x one interval)
+//     into a 3-deep staging ring; the four producer warps share an item (warp g = hidden units 8g..8g+7 = MN block g of U).
+// The tensor core adds into its fp32 accumulator with truncation (measured in round 1: 2.6e-3 relative drift over ~10^5
+// accumulations), so accumulation runs in chunks of kChunk items into two alternating TMEM sets; two fold warps add each
+// finished chunk into fp32 sums in shared memory with round-to-nearest adds, one chunk behind the tensor pipe.
+#include "tc_common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace tcde {
+namespace pg2 {
+
+using namespace umma;
+
+constexpr int H = 32, C = 8;
+constexpr int kPairs = 32;                 // (stage, path) pairs per item == K of one operand buffer
+constexpr int kN = 256, kM = 128;
+constexpr int kThreads = 256;              // warps 0-3 producers, 4-5 fold, 6 MMA issuer, 7 TMA
+constexpr int kBuf = 3, kStg = 3, kChunk = 16;
+constexpr int kParams = H * C * H + H * C;
+
+// shared memory map (bytes)
+constexpr int oA = 16384;                                // per buffer: A_hi (8 KB) | A_lo (8 KB) | B_hi (16 KB) | B_lo (16 KB)
+constexpr int kBufBytes = 49152;
+constexpr int oStg = kBuf * kBufBytes;                   // per stage: a (4 KB) | z (4 KB) | rows (4 KB)
+constexpr int kStgBytes = 12288;
+constexpr int oAcc = oStg + kStg * kStgBytes;            // fp32 sums [256 n][33 m]
+constexpr int oBars = oAcc + kN * 33 * 4;
+constexpr int kSmem = oBars + 256;
+
+// byte offset of (pair k, 16-byte chunk `chunk` of MN block `blk`) in an MN-major 128B-swizzled tile with 4 k-groups
+__device__ __forceinline__ uint32_t mn_off(int blk, int k, int chunk) {
+    return (uint32_t)(blk * 4096 + (k >> 3) * 1024 + (k & 7) * 128 + ((chunk ^ (k & 7)) << 4));
+}
+__device__ __forceinline__ uint64_t desc_mn(const void* tile) {     // LBO = 4096 B between MN blocks, SBO = 1024 B between k-groups
+    return (uint64_t)((smem_u32(tile) & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
+                 "l"(db), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// (x0, x1) -> packed bf16 hi parts and packed bf16 lo parts (x - hi, exact in fp32, then rounded)
+__device__ __forceinline__ void split_bf2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    lo = pack_bf2(x0 - h0, x1 - h1);
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ z_stages,
+                       const float* __restrict__ a_stages, const int32_t* __restrict__ stage_index, const float* __restrict__ stage_frac,
+                       const float* __restrict__ stage_weight, int n_stage_total, float* __restrict__ scratch, int64_t n_paths,
+                       const __grid_constant__ CUtensorMap rows_map) {
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+    uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem + oBars);      // [kStg]
+    uint64_t* stg_free = stg_full + kStg;                                 // [kStg]
+    uint64_t* full = stg_free + kStg;                                     // [kBuf]
+    uint64_t* empty = full + kBuf;                                        // [kBuf]
+    uint64_t* chunk_done = empty + kBuf;                                  // [2]
+    uint64_t* set_free = chunk_done + 2;                                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(set_free + 2);
+    float* acc = reinterpret_cast<float*>(smem + oAcc);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool cubic = (control_kind == TCDE_CONTROL_CUBIC);
+    const int row_floats = cubic ? 4 * C : C;
+
+    // ---- one-time setup: zero everything, then the constant parts of the A tiles (the ones row m = 32) -----------------
+    for (int e = tid; e < (oAcc + kN * 33 * 4) / 16; e += kThreads) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int e = tid; e < kBuf * kPairs; e += kThreads) {                 // A_hi[pair][m = 32] = 1.0 (bf16 0x3F80): chunk 4, element 0
+        const int b = e / kPairs, k = e % kPairs;
+        *reinterpret_cast<uint32_t*>(smem + b * kBufBytes + mn_off(0, k, 4)) = 0x3F80u;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStg; ++i) { mbar_init(&stg_full[i], 1); mbar_init(&stg_free[i], 128); }
+        for (int i = 0; i < kBuf; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&chunk_done[i], 1); mbar_init(&set_free[i], 33); }
+        fence_barrier_init();
+        tc::tma_prefetch_desc(&rows_map);
+    }
+    if (warp == 6) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_blocks = (n_paths + kPairs - 1) / kPairs;
+    const int64_t n_items = n_blocks * n_stage_total;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t n_mine = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+    const int64_t n_chunks = (n_mine + kChunk - 1) / kChunk;
+
+    if (warp == 7) {
+        // ================================ TMA: a, z, spline rows of item j -> staging ================================
+        if (lane == 0) {
+            for (int64_t j = 0; j < n_mine; ++j) {
+                const int s = (int)(j % kStg);
+                mbar_wait(&stg_free[s], (uint32_t)(((j / kStg) & 1) ^ 1));
+                const int64_t item = first + j * stride;
+                const int e = (int)(item / n_blocks);
+                const int64_t path0 = (item - (int64_t)e * n_blocks) * kPairs;
+                const int valid = (int)((n_paths - path0 < kPairs) ? (n_paths - path0) : kPairs);
+                unsigned char* dst = smem + oStg + s * kStgBytes;
+                tc::mbar_expect_tx(&stg_full[s], (uint32_t)(2 * valid * H * 4 + kPairs * row_floats * 4));
+                bulk_load(dst, a_stages + ((int64_t)e * n_paths + path0) * H, (uint32_t)(valid * H * 4), &stg_full[s]);
+                bulk_load(dst + 4096, z_stages + ((int64_t)e * n_paths + path0) * H, (uint32_t)(valid * H * 4), &stg_full[s]);
+                tc::tma_load_2d(dst + 8192, &rows_map, stage_index[e] * row_floats, (int)path0, &stg_full[s]);
+            }
+        }
+    } else if (warp == 6) {
+        // ================================ MMA issuer ===================================================================
+        if (lane == 0) {
+            // D = F32, A = B = BF16, both MN-major, N = 256, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+            for (int64_t j = 0; j < n_mine; ++j) {
+                const int b = (int)(j % kBuf);
+                const int64_t chunk = j / kChunk;
+                const int set = (int)(chunk & 1);
+                const bool opens = (j % kChunk) == 0, closes = (j % kChunk) == kChunk - 1 || j == n_mine - 1;
+                if (opens && chunk >= 2) mbar_wait(&set_free[set], (uint32_t)(((chunk >> 1) & 1) ^ 1));     // chunk - 2 has been folded
+                mbar_wait(&full[b], (uint32_t)((j / kBuf) & 1));
+                tc_fence_after();
+                unsigned char* buf = smem + b * kBufBytes;
+                const uint32_t d = tmem_base + (uint32_t)(set * kN);
+#pragma unroll
+                for (int kb = 0; kb < kPairs / 16; ++kb) {                // 16 pairs = 2 k-groups = 2 KB further into every MN block
+                    const uint64_t a_hi = desc_mn(buf + kb * 2048), a_lo = desc_mn(buf + 8192 + kb * 2048);
+                    const uint64_t b_hi = desc_mn(buf + oA + kb * 2048), b_lo = desc_mn(buf + oA + 16384 + kb * 2048);
+                    mma_bf16(d, a_lo, b_hi, idesc, (opens && kb == 0) ? 0u : 1u);      // small terms first
+                    mma_bf16(d, a_hi, b_lo, idesc, 1u);
+                    mma_bf16(d, a_hi, b_hi, idesc, 1u);
+                }
+                mma_commit(&empty[b]);
+                if (closes) mma_commit(&chunk_done[set]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ fold: finished chunks TMEM -> fp32 sums in shared memory ====================
+        // warp 4: lane m = row m of D (z index k); warp 5: lane 0 = row 32 (the ones row: dL/db)
+        const bool active = (warp == 4) || (lane == 0);
+        const int m = (warp == 4) ? lane : 32;
+        for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
+            const int set = (int)(chunk & 1);
+            if (active) {
+                mbar_wait(&chunk_done[set], (uint32_t)((chunk >> 1) & 1));
+                tc_fence_after();
+            }
+            __syncwarp();
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * kN);
+#pragma unroll 1
+            for (int q = 0; q < kN / 32; ++q) {
+                uint32_t v[32];
+                tmem_ld32_issue(taddr + 32 * q, v);                       // warp-wide (.sync.aligned); idle lanes discard
+                tmem_ld32_wait(v);
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[(32 * q + i) * 33 + m] += __uint_as_float(v[i]);
+                }
+            }
+            if (active) {
+                tc_fence_before();
+                mbar_arrive(&set_free[set]);
+            }
+        }
+    } else {
+        // ================================ producers: warp g = hidden units 8g .. 8g+7, lane = pair =====================
+        const int g = warp, p = lane;
+        for (int64_t j = 0; j < n_mine; ++j) {
+            const int s = (int)(j % kStg), b = (int)(j % kBuf);
+            const int64_t item = first + j * stride;
+            const int e = (int)(item / n_blocks);
+            const bool live = (item - (int64_t)e * n_blocks) * kPairs + p < n_paths;
+            const float we = stage_weight[e], fr = stage_frac[e];
+            mbar_wait(&stg_full[s], (uint32_t)((j / kStg) & 1));
+            const unsigned char* stg = smem + oStg + s * kStgBytes;
+            const float4 a0 = *reinterpret_cast<const float4*>(stg + p * 128 + g * 32), a1 = *reinterpret_cast<const float4*>(stg + p * 128 + g * 32 + 16);
+            const float4 z0 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + g * 32), z1 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + g * 32 + 16);
+            float dx[8];
+            if (cubic) {
+                const unsigned char* row = stg + 8192 + p * 128;          // [a | b | 2c | 3d], chunk c at position c ^ (p & 7)
+                const int x = p & 7;
+                const float4 b0 = *reinterpret_cast<const float4*>(row + ((2 ^ x) << 4)), b1 = *reinterpret_cast<const float4*>(row + ((3 ^ x) << 4));
+                const float4 c0 = *reinterpret_cast<const float4*>(row + ((4 ^ x) << 4)), c1 = *reinterpret_cast<const float4*>(row + ((5 ^ x) << 4));
+                const float4 d0 = *reinterpret_cast<const float4*>(row + ((6 ^ x) << 4)), d1 = *reinterpret_cast<const float4*>(row + ((7 ^ x) << 4));
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int c = 0; c < C; ++c)               // interpolation_cubic.py:331-336, then the stage's Runge-Kutta weight
+                    dx[c] = __fadd_rn(bb[c], __fmul_rn(__fadd_rn(cc[c], __fmul_rn(dd[c], fr)), fr)) * we;
+            } else {
+                const float4 b0 = *reinterpret_cast<const float4*>(stg + 8192 + p * 32), b1 = *reinterpret_cast<const float4*>(stg + 8192 + p * 32 + 16);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int c = 0; c < C; ++c) dx[c] = bb[c] * we;
+            }
+            mbar_arrive(&stg_free[s]);                                    // staging read into registers: the TMA warp may refill it
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            if (!live) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { av[i] = 0.f; zv[i] = 0.f; }
+            }
+            mbar_wait(&empty[b], (uint32_t)(((j / kBuf) & 1) ^ 1));       // the MMAs that last read this buffer are done
+            unsigned char* buf = smem + b * kBufBytes;
+            // U[pair][n = (8g + hh) * 8 + c] = a[hh] * dx[c]: one 16-byte chunk per hidden unit, MN block g, chunk hh
+#pragma unroll
+            for (int hh = 0; hh < 8; ++hh) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_bf2(av[hh] * dx[2 * q], av[hh] * dx[2 * q + 1], hi[q], lo[q]);
+                const uint32_t off = mn_off(g, p, hh);
+                *reinterpret_cast<uint4*>(buf + oA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(buf + oA + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            {   // Zx[pair][m = 8g .. 8g+7] = z: chunk g of MN block 0
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_bf2(zv[2 * q], zv[2 * q + 1], hi[q], lo[q]);
+                const uint32_t off = mn_off(0, p, g);
+                *reinterpret_cast<uint4*>(buf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(buf + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&full[b]);
+        }
+    }
+
+    // ---- epilogue: the CTA's sums -> its slot of the partial sums (field_vjp_reduce_kernel adds the slots up) -----------
+    tc_fence_before();
+    __syncthreads();
+    float* mine = scratch + (size_t)blockIdx.x * kParams;
+    for (int e = tid; e < kN * H; e += kThreads) {                        // dL/dW[n][k] = D[k][n]
+        const int n = e >> 5, k = e & 31;
+        mine[e] = acc[n * 33 + k];
+    }
+    for (int n = tid; n < kN; n += kThreads) mine[H * C * H + n] = acc[n * 33 + 32];
+    if (warp == 6) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace pg2
+
+int param_grad_bf16_grid(int64_t n_paths, int64_t n_stage_total) {
+    const int64_t items = ((n_paths + pg2::kPairs - 1) / pg2::kPairs) * n_stage_total;
+    int64_t g = sm_count();
+    if (g > items) g = items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, const float* z_stages, const float* a_stages,
+                        const int32_t* stage_index, const float* stage_frac, const float* stage_weight, int n_stage_total,
+                        float* scratch, int64_t n_paths, int grid, cudaStream_t stream) {
+    constexpr int smem = pg2::kSmem + 1024;                // slack for the 1024-byte alignment of the tiles
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    alignas(64) CUtensorMap rows_map;
+    const int row_floats = (control_kind == TCDE_CONTROL_CUBIC) ? 4 * pg2::C : pg2::C;
+    const int rc = tc::make_rows_tensor_map(&rows_map, control, n_paths, n_rows, row_floats, pg2::kPairs);
+    TCDE_CHECK_SUPPORTED(rc == 0, "parameter gradients: cuTensorMapEncodeTiled failed (%d)", rc);
+    pg2::param_grad_bf16_kernel<<<grid, pg2::kThreads, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index,
+                                                                      stage_frac, stage_weight, n_stage_total, scratch, n_paths, rows_map);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+}  // namespace tcde

@@ -56,7 +56,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // host: the tensor map of a control tensor (float32).  cuTensorMapEncodeTiled is taken from the driver through the runtime
 // (no link-time dependency on libcuda).  Returns cudaSuccess or an error.
-inline int make_rows_tensor_map(CUtensorMap* map, const float* control, int64_t n_paths, int64_t n_rows, int row_floats) {
+inline int make_rows_tensor_map(CUtensorMap* map, const float* control, int64_t n_paths, int64_t n_rows, int row_floats, int box_rows = 128) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -69,7 +69,7 @@ inline int make_rows_tensor_map(CUtensorMap* map, const float* control, int64_t 
     }
     const cuuint64_t dims[2] = {(cuuint64_t)(n_rows * row_floats), (cuuint64_t)n_paths};
     const cuuint64_t strides[1] = {(cuuint64_t)(n_rows * row_floats) * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)row_floats, 128u};
+    const cuuint32_t box[2] = {(cuuint32_t)row_floats, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUtensorMapSwizzle swz = (row_floats * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(control), dims, strides, box, estr,
