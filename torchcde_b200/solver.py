@@ -384,7 +384,9 @@ def _generic_solve_kernels(X, func, z0, t, method, step_size, is_prod, use_graph
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_out = run(static_in)
-        hit = (graph, static_in, static_out, func, X)      # func / X kept alive: their ids are the key
+        # func / X are kept alive because their ids are the key; ``run`` is kept because its closure owns the device
+        # copies of the schedule and of the control rows whose addresses the captured kernels read
+        hit = (graph, static_in, static_out, func, X, run)
         if len(_graphs) >= 8:
             _graphs.clear()
         _graphs[key] = hit
