@@ -385,7 +385,8 @@ def run_gpu_arm(args):
 
         note("end to end: {:.3f} ms per solve, matches={}".format(e2e_ms / e2e_steps, bool(e2e_ok)))
         # ---- secondary kernels (rank 0, N=1 only): the HBM-bound coefficient builders ---------
-        # ms = one public-API call (allocation, launch, NaN-flag read-back: a host sync); kernel_ms = the C-ABI
+        # ms = one public-API call (allocation, launch, and for the linear / natural builders the NaN-flag read-back that
+        # picks the reference's branch: a host sync; the Hermite builder reads nothing back); kernel_ms = the C-ABI
         # launch alone, 10 back to back (inputs + outputs are 5-20x the L2, so nothing is served from cache).
         # The roofline fraction is the kernel's; the API time is what a caller of the Python function sees.
         extra = {}
@@ -419,6 +420,12 @@ def run_gpu_arm(args):
                  lambda: _lib.call("tcde_linear_fill", _lib.ptr(xn), None, _lib.ptr(rows), BATCH, LENGTH, CHANNELS,
                                    code, _lib.ptr(flags), stream),
                  "one launch: tcde_linear_fill reports the NaN flag itself (8,192 R + 8,192 W per sequence)"),
+                ("hermite_bdiff_coeffs_30pct_nan", HERMITE_BYTES_PER_SEQ,
+                 lambda: cde.hermite_cubic_coefficients_with_backward_differences(xn),
+                 lambda: _lib.call("tcde_hermite_bdiff_coeffs_series", _lib.ptr(xn), None, _lib.ptr(rows), BATCH, LENGTH,
+                                   CHANNELS, code, None, stream),
+                 "one launch, no flag read-back: the gap fill happens in the warp's shared-memory tile "
+                 "(tcde_hermite_bdiff_coeffs_series; round 1: NaN-flag sync + fill + Hermite = 3 launches)"),
             )
             for name, nbytes, api_fn, abi_fn, remark in cases:
                 api_ms = time_loop(api_fn, 5, 3, device) / 5

@@ -70,6 +70,16 @@ TCDE_API int tcde_device_info(int* sm_count, int* cc_major, int* cc_minor);
 TCDE_API int tcde_hermite_bdiff_coeffs(const void* x, const void* t, void* coeffs, int64_t n_paths, int64_t length,
                               int64_t channels, int dtype, int32_t* flags, void* stream);
 
+/* hermite_cubic_coefficients_with_backward_differences of a series that MAY hold NaNs -- the whole reference function
+ * (interpolation_hermite_cubic_bdiff.py:23-44: linear_interpolation_coeffs at :33, then the coefficients at :36-43) as ONE
+ * launch: a warp holds a path in shared memory, fills its gaps in place (only if it has any) and writes the coefficient
+ * rows; the filled series never goes to HBM and no flag has to reach the host to pick a branch.  Bit-identical to
+ * tcde_linear_fill followed by tcde_hermite_bdiff_coeffs.  flags (optional): TCDE_FLAG_NAN_SEEN.
+ * TCDE_ERR_UNSUPPORTED when a path does not fit a warp's tile (channels > 32, or length x channels beyond ~3,000
+ * fp32 values): the caller runs the two kernels. */
+TCDE_API int tcde_hermite_bdiff_coeffs_series(const void* x, const void* t, void* coeffs, int64_t n_paths, int64_t length,
+                                     int64_t channels, int dtype, int32_t* flags, void* stream);
+
 /* linear_interpolation_coeffs with missing values, per series
  * (interpolation_linear.py:13-84): all-NaN -> zeros; missing ends take the first / last
  * observation; interior gaps are interpolated in time.  x -> out, same shape.  Bit-identical.

@@ -52,6 +52,6 @@ def run(batch, fused, method="rk4", reps=2):
 if __name__ == "__main__":
     b_fused = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     b_auto = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
-    rows = [run(b_fused, True), run(b_auto, False), run(b_auto, True)]
+    rows = [run(b_fused, True)] + ([run(b_auto, False), run(b_auto, True)] if b_auto > 0 else [])
     for r in rows:
         print(json.dumps(r))

@@ -153,3 +153,52 @@ def test_generic_field_kernel_loop_and_cuda_graph(method, step):
         assert torch.allclose(fast, slow, rtol=1e-5, atol=1e-5)
         assert torch.allclose(graph, fast, rtol=1e-6, atol=1e-6)
         assert torch.allclose(again, half, rtol=1e-6, atol=1e-6)          # the replay really read the new z0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(7, 256, 8), (5, 33, 3), (3, 2, 1), (4, 100, 32), (2, 700, 4), (6, 17, 5)])
+@pytest.mark.parametrize("with_t", [False, True])
+def test_fused_fill_and_hermite_is_bit_identical_to_the_two_kernels(dtype, shape, with_t):
+    """hermite_cubic_coefficients_with_backward_differences of a series with gaps is ONE launch
+    (tcde_hermite_bdiff_coeffs_series); it must reproduce tcde_linear_fill -> tcde_hermite_bdiff_coeffs bit for bit,
+    gaps at the ends, all-NaN channels and gap-free paths included."""
+    from torchcde_b200 import _lib
+    gen = torch.Generator(device=DEV).manual_seed(shape[1] * 31 + shape[2])
+    P, L, C = shape
+    x = torch.randn(P, L, C, generator=gen, device=DEV, dtype=dtype).cumsum(1)
+    hole = torch.rand(P, L, C, generator=gen, device=DEV) < 0.35
+    hole[0] = False                                       # a path without gaps
+    if P > 2:
+        hole[1, :, 0] = True                              # an all-NaN channel
+        hole[2, : L // 2, -1] = True                      # a missing start
+        hole[2, -1, 0] = True                             # a missing end
+    x = x.masked_fill(hole, float("nan"))
+    t = (torch.rand(L, generator=gen, device=DEV, dtype=dtype) + 0.1).cumsum(0) if with_t else None
+    code = _lib.dtype_code(dtype)
+    filled = torch.empty_like(x)
+    want = torch.empty(P, L - 1, 4 * C, device=DEV, dtype=dtype)
+    got = torch.full_like(want, float("nan"))
+    flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+    stream = _lib.stream_of(x)
+    _lib.call("tcde_linear_fill", _lib.ptr(x), _lib.ptr(t), _lib.ptr(filled), P, L, C, code, None, stream)
+    _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(filled), _lib.ptr(t), _lib.ptr(want), P, L, C, code, None, stream)
+    _lib.call("tcde_hermite_bdiff_coeffs_series", _lib.ptr(x), _lib.ptr(t), _lib.ptr(got), P, L, C, code, _lib.ptr(flags), stream)
+    assert bool(torch.isfinite(want).all())
+    assert torch.equal(got, want)
+    assert int(flags.item()) & _lib.FLAG_NAN_SEEN
+    # and the public builder (which now calls the fused entry) agrees with the differentiable restatement
+    pub = cde.hermite_cubic_coefficients_with_backward_differences(x, t)
+    assert torch.equal(pub, want)
+
+
+def test_fused_fill_and_hermite_reports_unsupported_shapes_and_the_builder_falls_back():
+    from torchcde_b200 import _lib
+    x = torch.randn(2, 9, 40, device=DEV)                 # channels > 32: no warp tile
+    x[0, 3, 5] = float("nan")
+    out = torch.empty(2, 8, 160, device=DEV)
+    with pytest.raises(NotImplementedError):
+        _lib.call("tcde_hermite_bdiff_coeffs_series", _lib.ptr(x), None, _lib.ptr(out), 2, 9, 40, _lib.dtype_code(x.dtype),
+                  None, _lib.stream_of(x))
+    got = cde.hermite_cubic_coefficients_with_backward_differences(x)
+    want = cde.hermite_cubic_coefficients_with_backward_differences(cde.linear_interpolation_coeffs(x))
+    assert bool(torch.isfinite(got).all()) and torch.equal(got, want)

@@ -202,12 +202,13 @@ def _hermite_kernel(x, t):
         out = torch.empty(p, length - 1, 4 * channels, dtype=flat.dtype, device=flat.device)
         if p == 0:
             return out.view(*batch, length - 1, 4 * channels)
-        flags = _flags(flat)
         stream = _lib.stream_of(flat)
-        _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length, channels,
-                  code, _lib.ptr(flags), stream)
-        if flags.item() & _lib.FLAG_NAN_SEEN:
-            # the reference fills first (bdiff.py:33); the kernel above told us it is needed
+        try:
+            # fill (where a path has gaps) + coefficients in one launch; nothing is read back, so the call is asynchronous
+            _lib.call("tcde_hermite_bdiff_coeffs_series", _lib.ptr(flat), _lib.ptr(knots), _lib.ptr(out), p, length,
+                      channels, code, None, stream)
+        except NotImplementedError:
+            # a path too large for a warp's tile: the reference's two passes (bdiff.py:33, :36-43), still without a sync
             filled = _fill(flat, knots)
             _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(filled), _lib.ptr(knots), _lib.ptr(out), p, length,
                       channels, code, None, stream)

@@ -240,7 +240,98 @@ template <> struct nan_code<double> {
 constexpr int kFillNone = 0x3FFFFF;          // no observation
 constexpr int kFillDist = 11;                // payload = distance to next observation | distance to next hole << 11
 
+// The in-place gap fill of ONE path held in a warp's shared-memory tile ([position][channel] order, chunk padding
+// ``padw``): shared by the stand-alone fill kernel and by the fused series -> Hermite kernel below.  Returns whether
+// this lane's chunk held a hole.  Must be called by the whole warp (shuffles); the caller separates it from the loads
+// and from the readers of the tile with __syncwarp().
 template <typename T, bool UNIT>
+__device__ __forceinline__ bool fill_tile_in_place(T* tile, const T* ts, int L, int C, int lgG,
+                                                   int padw, int lane) {
+    using E = exact<T>;
+    const int G = 1 << lgG;
+    const int nch = (L + G - 1) >> lgG;                     // chunks in use (<= 32 / C)
+    const int c = lane % C, j = lane / C;
+    const bool active = j < nch;
+    const int g0 = j << lgG, g1 = min(g0 + G, L);
+    const unsigned full = 0xffffffffu;
+    auto word = [&](int i) { return i * C + (i >> lgG) * padw; };
+    auto time_of = [&](int i) -> T { return UNIT ? T(i) : ts[i]; };
+    // backward: thread the holes (payload: distance to the next observation / next hole of the chunk, 0 = none)
+    int first_idx = kFillNone, last_idx = -1, head = -1;
+    T last_val = T(0);
+    if (active) {
+        T* ptr = tile + word(g1 - 1) + c;
+        for (int i = g1 - 1; i >= g0; --i, ptr -= C) {
+            const T w = *ptr;
+            if (is_nan(w)) {
+                const int d_obs = first_idx == kFillNone ? 0 : first_idx - i;
+                const int d_hole = head < 0 ? 0 : head - i;
+                *ptr = nan_code<T>::make(d_obs | (d_hole << kFillDist));
+                head = i;
+            } else {
+                if (last_idx < 0) { last_idx = i; last_val = w; }
+                first_idx = i;
+            }
+        }
+    }
+    // nearest observation in the chunks after (position) and before (position, value) this one
+    int after = kFillNone, before = -1;
+    T before_val = T(0);
+    for (int d = 1; d < nch; ++d) {
+        const int fa = __shfl_down_sync(full, first_idx, C * d);
+        const int la = __shfl_up_sync(full, last_idx, C * d);
+        const T lv = __shfl_up_sync(full, last_val, C * d);
+        if (after == kFillNone && j + d < nch) after = fa;
+        if (before < 0 && j - d >= 0) { before = la; before_val = lv; }
+    }
+    const int series_first = __shfl_sync(full, first_idx != kFillNone ? first_idx : after, c);
+    const int series_last = __shfl_sync(full, last_idx >= 0 ? last_idx : before, c + C * (nch - 1));
+    if (active) {
+        if (series_first == kFillNone) {                // nothing observed: the zero path (linear.py:19-21)
+            T* ptr = tile + word(g0) + c;
+            for (int i = g0; i < g1; ++i, ptr += C) *ptr = T(0);
+        } else {
+            const T v_first = tile[word(series_first) + c], v_last = tile[word(series_last) + c];
+            // the ends of the series count as observations carrying the first / last value (linear.py:31-34)
+            int prev_idx = before >= 0 ? before : 0;
+            T prev_val = before >= 0 ? before_val : v_first;
+            const int far_idx = after != kFillNone ? after : L - 1;
+            const T far_val = after != kFillNone ? tile[word(after) + c] : v_last;
+            T* base = tile + word(g0) + c;              // a chunk has no padding inside
+            T lo_t = T(0), span = T(1), rise = T(0);
+            for (int i = head, visited = -2; i >= 0;) {
+                T* ptr = base + (i - g0) * C;
+                const int code = nan_code<T>::get(*ptr);
+                const int d_obs = code & ((1 << kFillDist) - 1), d_hole = code >> kFillDist;
+                if (i != visited + 1) {                 // a new gap: fetch its end points
+                    if (i > g0) {
+                        prev_idx = i - 1;
+                        prev_val = ptr[-C];
+                    }
+                    const int hi_i = d_obs ? i + d_obs : far_idx;
+                    const T hi_v = d_obs ? ptr[d_obs * C] : far_val;
+                    lo_t = time_of(prev_idx);
+                    span = E::sub(time_of(hi_i), lo_t);
+                    rise = E::sub(hi_v, prev_val);
+                }
+                // linear.py:60-69: x[j] = lo + ((t_j - t_lo) / (t_hi - t_lo)) * (hi - lo)
+                *ptr = E::add(prev_val, E::mul(E::div(E::sub(time_of(i), lo_t), span), rise));
+                visited = i;
+                i = d_hole ? i + d_hole : -1;
+            }
+            // an imputed end point is a copy of the observation, not an interpolation
+            if (g0 == 0 && series_first > 0) tile[c] = v_first;
+            if (g1 == L && series_last < L - 1) tile[word(L - 1) + c] = v_last;
+        }
+    }
+    return head >= 0;
+}
+
+// OUT = 0: the filled series (linear_interpolation_coeffs).  OUT = 1: the Hermite coefficients with backward
+// differences of the filled series (interpolation_hermite_cubic_bdiff.py:23-44 = fill, then :8-20) straight from the
+// warp's tile -- one launch, the filled series never goes to HBM, and no NaN flag has to travel to the host to decide
+// whether a fill is needed: a path without holes skips the fill (one vote per path after the loads).
+template <typename T, bool UNIT, int OUT>
 __global__ void __launch_bounds__(kThreads)
 linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_paths, int L,
                         int C, int lgG, int padw, int tile_words, int32_t* __restrict__ flags) {
@@ -254,14 +345,8 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* tile = tiles + (size_t)warp * tile_words;
-    const int G = 1 << lgG;
-    const int nch = (L + G - 1) >> lgG;                     // chunks in use (<= 32 / C)
-    const int c = lane % C, j = lane / C;
-    const bool active = j < nch;
-    const int g0 = j << lgG, g1 = min(g0 + G, L);
     const unsigned full = 0xffffffffu;
     auto word = [&](int i) { return i * C + (i >> lgG) * padw; };
-    auto time_of = [&](int i) -> T { return UNIT ? T(i) : ts[i]; };
     const bool vec4 = (sizeof(T) == 4) && ((C & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const int Q = C >> 2;
@@ -270,15 +355,17 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
 
     for (int64_t p = (int64_t)blockIdx.x * (kThreads / 32) + warp; p < n_paths; p += warps_total) {
         const T* xg = x + p * (int64_t)L * C;
-        T* og = out + p * (int64_t)L * C;
         __syncwarp();                                       // the previous path has been copied out
+        bool hole = false;
         if (vec4) {
             const float4* xg4 = reinterpret_cast<const float4*>(xg);
             const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
             int i = lane / Q, q = lane - (lane / Q) * Q;
 #pragma unroll 8
             for (int e = lane; e < L * Q; e += 32) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(tile) + word(i) + 4 * q) = __ldg(xg4 + e);
+                const float4 v = __ldg(xg4 + e);
+                hole |= is_nan(v.x) | is_nan(v.y) | is_nan(v.z) | is_nan(v.w);
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(tile) + word(i) + 4 * q) = v;
                 i += dq_i;
                 q += dq_q;
                 if (q >= Q) { q -= Q; ++i; }
@@ -288,103 +375,127 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
             int i = lane / C, cc = lane - (lane / C) * C;
 #pragma unroll 4
             for (int e = lane; e < L * C; e += 32) {
-                tile[word(i) + cc] = xg[e];
+                const T v = xg[e];
+                hole |= is_nan(v);
+                tile[word(i) + cc] = v;
                 i += di;
                 cc += dc;
                 if (cc >= C) { cc -= C; ++i; }
             }
         }
         __syncwarp();
-        // backward: thread the holes (payload: distance to the next observation / next hole of the chunk, 0 = none)
-        int first_idx = kFillNone, last_idx = -1, head = -1;
-        T last_val = T(0);
-        if (active) {
-            T* ptr = tile + word(g1 - 1) + c;
-            for (int i = g1 - 1; i >= g0; --i, ptr -= C) {
-                const T w = *ptr;
-                if (is_nan(w)) {
-                    const int d_obs = first_idx == kFillNone ? 0 : first_idx - i;
-                    const int d_hole = head < 0 ? 0 : head - i;
-                    *ptr = nan_code<T>::make(d_obs | (d_hole << kFillDist));
-                    head = i;
-                } else {
-                    if (last_idx < 0) { last_idx = i; last_val = w; }
-                    first_idx = i;
-                }
-            }
+        if (__any_sync(full, hole)) {
+            saw_nan = true;
+            fill_tile_in_place<T, UNIT>(tile, ts, L, C, lgG, padw, lane);
+            __syncwarp();
         }
-        saw_nan |= head >= 0;
-        // nearest observation in the chunks after (position) and before (position, value) this one
-        int after = kFillNone, before = -1;
-        T before_val = T(0);
-        for (int d = 1; d < nch; ++d) {
-            const int fa = __shfl_down_sync(full, first_idx, C * d);
-            const int la = __shfl_up_sync(full, last_idx, C * d);
-            const T lv = __shfl_up_sync(full, last_val, C * d);
-            if (after == kFillNone && j + d < nch) after = fa;
-            if (before < 0 && j - d >= 0) { before = la; before_val = lv; }
-        }
-        const int series_first = __shfl_sync(full, first_idx != kFillNone ? first_idx : after, c);
-        const int series_last = __shfl_sync(full, last_idx >= 0 ? last_idx : before, c + C * (nch - 1));
-        if (active) {
-            if (series_first == kFillNone) {                // nothing observed: the zero path (linear.py:19-21)
-                T* ptr = tile + word(g0) + c;
-                for (int i = g0; i < g1; ++i, ptr += C) *ptr = T(0);
-            } else {
-                const T v_first = tile[word(series_first) + c], v_last = tile[word(series_last) + c];
-                // the ends of the series count as observations carrying the first / last value (linear.py:31-34)
-                int prev_idx = before >= 0 ? before : 0;
-                T prev_val = before >= 0 ? before_val : v_first;
-                const int far_idx = after != kFillNone ? after : L - 1;
-                const T far_val = after != kFillNone ? tile[word(after) + c] : v_last;
-                T* base = tile + word(g0) + c;              // a chunk has no padding inside
-                T lo_t = T(0), span = T(1), rise = T(0);
-                for (int i = head, visited = -2; i >= 0;) {
-                    T* ptr = base + (i - g0) * C;
-                    const int code = nan_code<T>::get(*ptr);
-                    const int d_obs = code & ((1 << kFillDist) - 1), d_hole = code >> kFillDist;
-                    if (i != visited + 1) {                 // a new gap: fetch its end points
-                        if (i > g0) {
-                            prev_idx = i - 1;
-                            prev_val = ptr[-C];
-                        }
-                        const int hi_i = d_obs ? i + d_obs : far_idx;
-                        const T hi_v = d_obs ? ptr[d_obs * C] : far_val;
-                        lo_t = time_of(prev_idx);
-                        span = E::sub(time_of(hi_i), lo_t);
-                        rise = E::sub(hi_v, prev_val);
-                    }
-                    // linear.py:60-69: x[j] = lo + ((t_j - t_lo) / (t_hi - t_lo)) * (hi - lo)
-                    *ptr = E::add(prev_val, E::mul(E::div(E::sub(time_of(i), lo_t), span), rise));
-                    visited = i;
-                    i = d_hole ? i + d_hole : -1;
-                }
-                // an imputed end point is a copy of the observation, not an interpolation
-                if (g0 == 0 && series_first > 0) tile[c] = v_first;
-                if (g1 == L && series_last < L - 1) tile[word(L - 1) + c] = v_last;
-            }
-        }
-        __syncwarp();
-        if (vec4) {
-            float4* og4 = reinterpret_cast<float4*>(og);
-            const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
-            int i = lane / Q, q = lane - (lane / Q) * Q;
+        if (OUT == 0) {
+            T* og = out + p * (int64_t)L * C;
+            if (vec4) {
+                float4* og4 = reinterpret_cast<float4*>(og);
+                const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
+                int i = lane / Q, q = lane - (lane / Q) * Q;
 #pragma unroll 8
-            for (int e = lane; e < L * Q; e += 32) {
-                og4[e] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tile) + word(i) + 4 * q);
-                i += dq_i;
-                q += dq_q;
-                if (q >= Q) { q -= Q; ++i; }
+                for (int e = lane; e < L * Q; e += 32) {
+                    og4[e] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tile) + word(i) + 4 * q);
+                    i += dq_i;
+                    q += dq_q;
+                    if (q >= Q) { q -= Q; ++i; }
+                }
+            } else {
+                const int di = 32 / C, dc = 32 - di * C;
+                int i = lane / C, cc = lane - (lane / C) * C;
+#pragma unroll 4
+                for (int e = lane; e < L * C; e += 32) {
+                    og[e] = tile[word(i) + cc];
+                    i += di;
+                    cc += dc;
+                    if (cc >= C) { cc -= C; ++i; }
+                }
             }
         } else {
-            const int di = 32 / C, dc = 32 - di * C;
-            int i = lane / C, cc = lane - (lane / C) * C;
-#pragma unroll 4
-            for (int e = lane; e < L * C; e += 32) {
-                og[e] = tile[word(i) + cc];
-                i += di;
-                cc += dc;
-                if (cc >= C) { cc -= C; ++i; }
+            // interval r of channel c: (a, b, 2c, 3d) from the knots r-1, r, r+1 (operation order of bdiff.py:8-20, :36-43)
+            T* og = out + p * (int64_t)(L - 1) * 4 * C;
+            if (vec4) {
+                float4* og4 = reinterpret_cast<float4*>(og);
+                const float* tf = reinterpret_cast<const float*>(tile);
+                const float* tsf = reinterpret_cast<const float*>(ts);
+                const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
+                int r = lane / Q, q = lane - (lane / Q) * Q;
+#pragma unroll 2
+                for (int e = lane; e < (L - 1) * Q; e += 32) {
+                    const float4 lo = *reinterpret_cast<const float4*>(tf + word(r) + 4 * q);
+                    const float4 hi = *reinterpret_cast<const float4*>(tf + word(r + 1) + 4 * q);
+                    const float4 pp = (r > 0) ? *reinterpret_cast<const float4*>(tf + word(r - 1) + 4 * q) : lo;
+                    const float xl[4] = {lo.x, lo.y, lo.z, lo.w}, xh[4] = {hi.x, hi.y, hi.z, hi.w};
+                    const float xq[4] = {pp.x, pp.y, pp.z, pp.w};
+                    float b[4], c2[4], d3[4];
+                    float dt = 1.f, dtp = 1.f, inv_sq = 1.f;
+                    if (!UNIT) {
+                        dt = exact<float>::sub(tsf[r + 1], tsf[r]);
+                        dtp = (r > 0) ? exact<float>::sub(tsf[r], tsf[r - 1]) : dt;
+                        inv_sq = exact<float>::div(1.f, exact<float>::mul(dt, dt));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        using F = exact<float>;
+                        if (UNIT) {
+                            const float dn = F::sub(xh[k], xl[k]);
+                            const float dp = (r > 0) ? F::sub(xl[k], xq[k]) : dn;
+                            const float bend = F::sub(dn, dp);
+                            c2[k] = F::mul(2.f, F::add(F::sub(F::mul(3.f, bend), dn), dp));
+                            d3[k] = F::sub(bend, c2[k]);
+                            b[k] = dp;
+                        } else {
+                            const float dn = F::div(F::sub(xh[k], xl[k]), dt);
+                            const float dp = (r > 0) ? F::div(F::sub(xl[k], xq[k]), dtp) : dn;
+                            const float inner = F::add(F::sub(F::mul(3.f, F::sub(dn, dp)), dn), dp);
+                            c2[k] = F::div(F::mul(2.f, inner), dt);
+                            d3[k] = F::sub(F::mul(inv_sq, F::sub(dn, dp)), F::div(c2[k], dt));
+                            b[k] = dp;
+                        }
+                    }
+                    float4* row = og4 + (size_t)r * 4 * Q + q;
+                    __stcs(row, lo);
+                    __stcs(row + Q, make_float4(b[0], b[1], b[2], b[3]));
+                    __stcs(row + 2 * Q, make_float4(c2[0], c2[1], c2[2], c2[3]));
+                    __stcs(row + 3 * Q, make_float4(d3[0], d3[1], d3[2], d3[3]));
+                    r += dq_i;
+                    q += dq_q;
+                    if (q >= Q) { q -= Q; ++r; }
+                }
+            } else {
+                const int di = 32 / C, dc = 32 - di * C;
+                int r = lane / C, cc = lane - (lane / C) * C;
+                for (int e = lane; e < (L - 1) * C; e += 32) {
+                    const T xl = tile[word(r) + cc], xh = tile[word(r + 1) + cc];
+                    T b, two_c, three_d;
+                    if (UNIT) {
+                        const T dn = E::sub(xh, xl);
+                        const T dp = (r > 0) ? E::sub(xl, tile[word(r - 1) + cc]) : dn;
+                        const T bend = E::sub(dn, dp);
+                        two_c = E::mul(T(2), E::add(E::sub(E::mul(T(3), bend), dn), dp));
+                        three_d = E::sub(bend, two_c);
+                        b = dp;
+                    } else {
+                        const T dt = E::sub(ts[r + 1], ts[r]);
+                        const T dn = E::div(E::sub(xh, xl), dt);
+                        const T dp = (r > 0) ? E::div(E::sub(xl, tile[word(r - 1) + cc]), E::sub(ts[r], ts[r - 1])) : dn;
+                        const T inner = E::add(E::sub(E::mul(T(3), E::sub(dn, dp)), dn), dp);
+                        two_c = E::div(E::mul(T(2), inner), dt);
+                        const T inv_sq = E::div(T(1), E::mul(dt, dt));
+                        three_d = E::sub(E::mul(inv_sq, E::sub(dn, dp)), E::div(two_c, dt));
+                        b = dp;
+                    }
+                    T* row = og + (size_t)r * 4 * C + cc;
+                    row[0] = xl;
+                    row[C] = b;
+                    row[2 * C] = two_c;
+                    row[3 * C] = three_d;
+                    r += di;
+                    cc += dc;
+                    if (cc >= C) { cc -= C; ++r; }
+                }
             }
         }
     }
@@ -448,9 +559,57 @@ nan_flag_kernel(const T* __restrict__ x, int64_t n, int32_t* __restrict__ flags)
 int g_fill_variant = 0;
 int g_natural_variant = 0;
 
+// Launch of the scan kernel (OUT = 0 filled series, 1 Hermite coefficients); TCDE_ERR_UNSUPPORTED (without setting an error
+// message) when the shape does not fit a warp's shared-memory tile.
+static int launch_fill_scan(const void* x, const void* t, void* out, int64_t n_paths, int L, int C, int dtype,
+                            int32_t* flags, cudaStream_t s, int what) {
+    if (!(C <= 32 && L < kFillNone)) return TCDE_ERR_UNSUPPORTED;
+    // lane = (channel, chunk of positions), tile in the global layout
+    const size_t elem = (dtype == TCDE_F32) ? 4 : 8;
+    const int n_chunks = 32 / C;
+    int lgG = 0;
+    while ((1 << lgG) * n_chunks < L) ++lgG;
+    const int G = 1 << lgG;
+    const int nct = (L + G - 1) / G;
+    const int bank_words = (int)(128 / elem);
+    const int padw = (int)((((int64_t)C - (int64_t)G * C) % bank_words + bank_words) % bank_words);
+    const int tile_words = (L * C + nct * padw + 3) & ~3;
+    const size_t smem = (t ? (size_t)((L + 3) & ~3) * elem : 0) + (size_t)(kThreads / 32) * tile_words * elem;
+    if (!(smem <= 100 * 1024 && lgG < kFillDist)) return TCDE_ERR_UNSUPPORTED;   // hole-list distances are 11-bit
+    const void* kern;
+    if (what == 0)
+        kern = (dtype == TCDE_F32)
+            ? (t ? (const void*)linear_fill_scan_kernel<float, false, 0> : (const void*)linear_fill_scan_kernel<float, true, 0>)
+            : (t ? (const void*)linear_fill_scan_kernel<double, false, 0> : (const void*)linear_fill_scan_kernel<double, true, 0>);
+    else
+        kern = (dtype == TCDE_F32)
+            ? (t ? (const void*)linear_fill_scan_kernel<float, false, 1> : (const void*)linear_fill_scan_kernel<float, true, 1>)
+            : (t ? (const void*)linear_fill_scan_kernel<double, false, 1> : (const void*)linear_fill_scan_kernel<double, true, 1>);
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = persistent_grid(kern, kThreads, smem, (n_paths + kThreads / 32 - 1) / (kThreads / 32));
+    const int Li = L, Ci = C;
+    void* args[] = {(void*)&x, (void*)&t, (void*)&out, (void*)&n_paths, (void*)&Li, (void*)&Ci, (void*)&lgG,
+                    (void*)&padw, (void*)&tile_words, (void*)&flags};
+    TCDE_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, smem, s));
+    return TCDE_OK;
+}
+
+
 }  // namespace tcde
 
 using namespace tcde;
+
+extern "C" int tcde_hermite_bdiff_coeffs_series(const void* x, const void* t, void* coeffs, int64_t n_paths, int64_t length,
+                                                int64_t channels, int dtype, int32_t* flags, void* stream) {
+    int rc = check_shape(x, coeffs, n_paths, length, channels, dtype);
+    if (rc != TCDE_OK) return rc;
+    if (n_paths == 0) return TCDE_OK;
+    rc = launch_fill_scan(x, t, coeffs, n_paths, (int)length, (int)channels, dtype, flags, static_cast<cudaStream_t>(stream), 1);
+    TCDE_CHECK_SUPPORTED(rc != TCDE_ERR_UNSUPPORTED,
+                         "fused fill + Hermite: a path of length=%lld x channels=%lld does not fit a warp's shared-memory tile "
+                         "(run tcde_linear_fill, then tcde_hermite_bdiff_coeffs)", (long long)length, (long long)channels);
+    return rc;
+}
 
 extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t n_paths, int64_t length,
                                 int64_t channels, int dtype, int32_t* flags, void* stream) {
@@ -460,30 +619,9 @@ extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t
     if (n_series == 0) return TCDE_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int L = (int)length, C = (int)channels;
-    if (C <= 32 && L < kFillNone && g_fill_variant == 0) {
-        // scan kernel: lane = (channel, chunk of positions), tile in the global layout
-        const size_t elem = (dtype == TCDE_F32) ? 4 : 8;
-        const int n_chunks = 32 / C;
-        int lgG = 0;
-        while ((1 << lgG) * n_chunks < L) ++lgG;
-        const int G = 1 << lgG;
-        const int nct = (L + G - 1) / G;
-        const int bank_words = (int)(128 / elem);
-        const int padw = (int)((((int64_t)C - (int64_t)G * C) % bank_words + bank_words) % bank_words);
-        const int tile_words = (L * C + nct * padw + 3) & ~3;
-        const size_t smem = (t ? (size_t)((L + 3) & ~3) * elem : 0) + (size_t)(kThreads / 32) * tile_words * elem;
-        if (smem <= 100 * 1024 && lgG < kFillDist) {          // hole-list distances are 11-bit
-            const void* kern = (dtype == TCDE_F32)
-                ? (t ? (const void*)linear_fill_scan_kernel<float, false> : (const void*)linear_fill_scan_kernel<float, true>)
-                : (t ? (const void*)linear_fill_scan_kernel<double, false> : (const void*)linear_fill_scan_kernel<double, true>);
-            TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = persistent_grid(kern, kThreads, smem, (n_paths + kThreads / 32 - 1) / (kThreads / 32));
-            const int Li = L, Ci = C;
-            void* args[] = {(void*)&x, (void*)&t, (void*)&out, (void*)&n_paths, (void*)&Li, (void*)&Ci, (void*)&lgG,
-                            (void*)&padw, (void*)&tile_words, (void*)&flags};
-            TCDE_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, smem, s));
-            return TCDE_OK;
-        }
+    if (g_fill_variant == 0) {
+        rc = launch_fill_scan(x, t, out, n_paths, L, C, dtype, flags, s, 0);
+        if (rc != TCDE_ERR_UNSUPPORTED) return rc;
     }
     if (flags != nullptr) {               // the other kernels do not report: a separate pass over x
         rc = tcde_nan_flag(x, n_series * L, dtype, flags, stream);

@@ -83,9 +83,16 @@ class SeriesPipeline:
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n)]
         self.x = [torch.empty(chunk_paths, length, channels, dtype=dtype, device=self.device) for _ in range(n)]
         self.z0 = [torch.empty(chunk_paths, hidden, dtype=dtype, device=self.device) for _ in range(n)]
-        self.filled = [torch.empty(chunk_paths, length, channels, dtype=dtype, device=self.device) for _ in range(n)]
+        self.fused_builder = True              # tcde_hermite_bdiff_coeffs_series until it reports UNSUPPORTED
+        self.filled = [None] * n               # staging of the two-launch builder, allocated only if that is needed
         self.coeffs = [torch.empty(chunk_paths, length - 1, 4 * channels, dtype=dtype, device=self.device)
                        for _ in range(n)]
+
+
+    def filled_slot(self, slot):
+        if self.filled[slot] is None:
+            self.filled[slot] = torch.empty_like(self.x[slot])
+        return self.filled[slot]
 
 
 _series_pipelines = {}
@@ -97,8 +104,9 @@ def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths
     (``hermite_cubic_coefficients_with_backward_differences``'s kernel), solve, copy the result out.
     Moving ``x`` instead of its coefficients cuts the PCIe traffic 4x; rebuilding the coefficients
     costs ~0.5 ms per 65,536 paths on the device.  Missing values (NaN) are handled like the public builder does
-    (interpolation_hermite_cubic_bdiff.py:33: linear gap filling first) -- the fill kernel always runs (0.3 ms per
-    65,536 series, a copy when nothing is missing), so no NaN flag has to travel back to the host mid-pipeline."""
+    (interpolation_hermite_cubic_bdiff.py:33: linear gap filling first) -- inside the same launch
+    (``tcde_hermite_bdiff_coeffs_series``: a warp fills its path in shared memory when it has gaps), so no NaN flag has to
+    travel back to the host mid-pipeline."""
     device = torch.device(device if device is not None else "cuda")
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
@@ -126,13 +134,21 @@ def cdeint_from_host_series(x_host, func, z0_host, t, out_host=None, chunk_paths
             slot = i % pipe.SLOTS
             with torch.cuda.stream(pipe.streams[slot]):
                 n = hi - lo
-                x_dev, z_dev, coeffs, filled = pipe.x[slot][:n], pipe.z0[slot][:n], pipe.coeffs[slot][:n], pipe.filled[slot][:n]
+                x_dev, z_dev, coeffs = pipe.x[slot][:n], pipe.z0[slot][:n], pipe.coeffs[slot][:n]
                 x_dev.copy_(x_host[lo:hi], non_blocking=True)
                 z_dev.copy_(z0_host[lo:hi], non_blocking=True)
-                _lib.call("tcde_linear_fill", _lib.ptr(x_dev), None, _lib.ptr(filled), n, length, channels, code, None,
-                          _lib.stream_of(x_dev))
-                _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(filled), None, _lib.ptr(coeffs), n, length, channels,
-                          code, None, _lib.stream_of(x_dev))
+                if pipe.fused_builder:
+                    try:
+                        _lib.call("tcde_hermite_bdiff_coeffs_series", _lib.ptr(x_dev), None, _lib.ptr(coeffs), n, length,
+                                  channels, code, None, _lib.stream_of(x_dev))
+                    except NotImplementedError:
+                        pipe.fused_builder = False            # a path does not fit a warp's tile: two launches
+                if not pipe.fused_builder:
+                    filled = pipe.filled_slot(slot)[:n]
+                    _lib.call("tcde_linear_fill", _lib.ptr(x_dev), None, _lib.ptr(filled), n, length, channels, code, None,
+                              _lib.stream_of(x_dev))
+                    _lib.call("tcde_hermite_bdiff_coeffs", _lib.ptr(filled), None, _lib.ptr(coeffs), n, length, channels,
+                              code, None, _lib.stream_of(x_dev))
                 out = cdeint(CubicSpline(coeffs), func, z_dev, t_cpu, **kwargs)
                 out_host[lo:hi].copy_(out, non_blocking=True)
     for s in pipe.streams:
