@@ -20,7 +20,7 @@ def problem(B):
 with torch.no_grad():
     X, func, z0 = problem(148 * 256)          # exactly one CTA per SM, both tiles live
     trace = torch.zeros(64, 8, dtype=torch.int64, device=dev)
-    for variant in (4, 3):
+    for variant in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '4,3').split(',')]:
         _lib.call("tcde_set_solve_variant", variant)
         cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options=opts)
         trace.zero_()
@@ -40,7 +40,7 @@ with torch.no_grad():
                   f(tr[20:40, 4] - tr[20:40, 3]), f(tr[20:40, 5] - tr[20:40, 4]), f(tr[20:40, 6] - tr[20:40, 5]),
                   f(tr[21:41, 2] - tr[20:40, 6])))
     X, func, z0 = problem(65536)
-    for variant in (0, 4 + 16 * 64, 4 + 16 * 16, 4 + 16 * (16 + 64), 3, 2):
+    for variant in [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else '0,1028,260,1284,3,2').split(',')]:
         _lib.call("tcde_set_solve_variant", variant)
         for _ in range(2):
             cde.cdeint(X, func, z0, t, adjoint=False, method="rk4", options=opts)

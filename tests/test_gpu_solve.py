@@ -256,7 +256,7 @@ def _set_variant(v):
     _lib.call("tcde_set_solve_variant", v)
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 32])
+@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 32, 5, 5 + 16 * 32])
 @pytest.mark.parametrize("batch", [1, 100, 128, 129, 256, 300, 1000])
 def test_tensor_core_variant_matches_cuda_core_and_oracle(batch, variant):
     """The tcgen05 kernels -- 2: solve_umma.cu (round 1, 3xTF32), 3 / 4: solve_tc.cu (Runge-Kutta state in registers;
@@ -294,7 +294,7 @@ def test_tensor_core_variant_matches_cuda_core_and_oracle(batch, variant):
         _set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 16])
+@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 16, 5])
 def test_tensor_core_variant_full_size(variant):
     gen = torch.Generator(device=DEV).manual_seed(0)
     B, L, C, H = 65536, 256, 8, 32
@@ -321,7 +321,7 @@ def test_tensor_core_variant_full_size(variant):
         _set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 4 + 16 * 32])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 4 + 16 * 32, 5, 5 + 16 * 32])
 def test_decreasing_output_times(variant):
     """A decreasing t is integrated as -t with the field negated (torchdiffeq's time reversal)."""
     length, channels, hidden, batch = 20, 8, 32, 70

@@ -117,6 +117,8 @@ int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
 // round-2 kernel (solve_tc.cu): Runge-Kutta state in registers; mode 0 = 3xTF32 (13 MMAs per stage), mode 1 = 2xFP16 with
 // per-path power-of-two scaling (7 MMAs per stage)
 int solve_tc_f32(const UmmaArgs& a, int H, int C, int mode, cudaStream_t stream);
+// solve_tc2.cu: mode 1 with two threads per path (each owns half of the hidden state); no stage dump
+int solve_tc2_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
 int current_solve_variant();          // tcde_set_solve_variant: 0 auto, 1 CUDA-core, 2 tcgen05 round 1, 3 tcgen05 TF32 r2, 4 tcgen05 FP16 r2
 
 // parameter gradients of a whole backward solve on the tensor cores (param_grad_umma.cu)

@@ -13,8 +13,10 @@
 //     pair's row -- 128-bit stores straight into the canonical layout (8 k-rows x 128 B atoms, 128B swizzle), no transpose;
 //   * BF16 operands with a two-way split (hi + lo: z_lo.U_hi + z_hi.U_lo + z_hi.U_hi, error ~2^-16 per product -- a gradient
 //     needs no more, and unlike FP16 no scaling is needed: a per-pair scale cannot be factored out of a sum over pairs);
-//   * a, z and the spline rows of an item arrive by TMA (two 4 KB bulk copies + one tensor box of 32 paths x one interval)
-//     into a 3-deep staging ring; the four producer warps share an item (warp g = hidden units 8g..8g+7 = MN block g of U).
+//   * a, z and the spline rows of an item arrive by TMA (three tensor boxes of 32 paths, 128-byte swizzle: the producers'
+//     128-bit reads of their own row are bank-conflict free -- linear rows cost 8 wavefronts per load, ncu: 58 % LSU) into
+//     a 3-deep staging ring; the eight producer warps share an item (warp = MN block g of U = hidden units 8g..8g+7,
+//     half of it: four 16-byte chunks).  Four producer warps needed ~1,900 cycles per item against 768 of tensor pipe.
 // The tensor core adds into its fp32 accumulator with truncation (measured in round 1: 2.6e-3 relative drift over ~10^5
 // accumulations), so accumulation runs in chunks of kChunk items into two alternating TMEM sets; two fold warps add each
 // finished chunk into fp32 sums in shared memory with round-to-nearest adds, one chunk behind the tensor pipe.
@@ -30,7 +32,8 @@ using namespace umma;
 constexpr int H = 32, C = 8;
 constexpr int kPairs = 32;                 // (stage, path) pairs per item == K of one operand buffer
 constexpr int kN = 256, kM = 128;
-constexpr int kThreads = 256;              // warps 0-3 producers, 4-5 fold, 6 MMA issuer, 7 TMA
+constexpr int kProducers = 256;            // threads of warps 0-7
+constexpr int kThreads = 384;              // warps 0-7 producers, 8-9 fold, 10 MMA issuer, 11 TMA
 constexpr int kBuf = 3, kStg = 3, kChunk = 16;
 constexpr int kParams = H * C * H + H * C;
 
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ z_stages,
                        const float* __restrict__ a_stages, const int32_t* __restrict__ stage_index, const float* __restrict__ stage_frac,
                        const float* __restrict__ stage_weight, int n_stage_total, float* __restrict__ scratch, int64_t n_paths,
-                       const __grid_constant__ CUtensorMap rows_map) {
+                       const __grid_constant__ CUtensorMap rows_map, const __grid_constant__ CUtensorMap a_map,
+                       const __grid_constant__ CUtensorMap z_map) {
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem + oBars);      // [kStg]
@@ -99,13 +103,15 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         *reinterpret_cast<uint32_t*>(smem + b * kBufBytes + mn_off(0, k, 4)) = 0x3F80u;
     }
     if (tid == 0) {
-        for (int i = 0; i < kStg; ++i) { mbar_init(&stg_full[i], 1); mbar_init(&stg_free[i], 128); }
-        for (int i = 0; i < kBuf; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kStg; ++i) { mbar_init(&stg_full[i], 1); mbar_init(&stg_free[i], kProducers); }
+        for (int i = 0; i < kBuf; ++i) { mbar_init(&full[i], kProducers); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&chunk_done[i], 1); mbar_init(&set_free[i], 33); }
         fence_barrier_init();
         tc::tma_prefetch_desc(&rows_map);
+        tc::tma_prefetch_desc(&a_map);
+        tc::tma_prefetch_desc(&z_map);
     }
-    if (warp == 6) tmem_alloc(tmem_slot, 512);
+    if (warp == 10) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -118,7 +124,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
     const int64_t n_mine = first < n_items ? (n_items - first + stride - 1) / stride : 0;
     const int64_t n_chunks = (n_mine + kChunk - 1) / kChunk;
 
-    if (warp == 7) {
+    if (warp == 11) {
         // ================================ TMA: a, z, spline rows of item j -> staging ================================
         if (lane == 0) {
             for (int64_t j = 0; j < n_mine; ++j) {
@@ -127,15 +133,15 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 const int64_t item = first + j * stride;
                 const int e = (int)(item / n_blocks);
                 const int64_t path0 = (item - (int64_t)e * n_blocks) * kPairs;
-                const int valid = (int)((n_paths - path0 < kPairs) ? (n_paths - path0) : kPairs);
                 unsigned char* dst = smem + oStg + s * kStgBytes;
-                tc::mbar_expect_tx(&stg_full[s], (uint32_t)(2 * valid * H * 4 + kPairs * row_floats * 4));
-                bulk_load(dst, a_stages + ((int64_t)e * n_paths + path0) * H, (uint32_t)(valid * H * 4), &stg_full[s]);
-                bulk_load(dst + 4096, z_stages + ((int64_t)e * n_paths + path0) * H, (uint32_t)(valid * H * 4), &stg_full[s]);
+                // boxes are always delivered whole (rows beyond n_paths arrive as zeros)
+                tc::mbar_expect_tx(&stg_full[s], (uint32_t)(2 * kPairs * H * 4 + kPairs * row_floats * 4));
+                tc::tma_load_3d(dst, &a_map, 0, (int)path0, e, &stg_full[s]);
+                tc::tma_load_3d(dst + 4096, &z_map, 0, (int)path0, e, &stg_full[s]);
                 tc::tma_load_2d(dst + 8192, &rows_map, stage_index[e] * row_floats, (int)path0, &stg_full[s]);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // ================================ MMA issuer ===================================================================
         if (lane == 0) {
             // D = F32, A = B = BF16, both MN-major, N = 256, M = 128
@@ -162,11 +168,11 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 if (closes) mma_commit(&chunk_done[set]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 8) {
         // ================================ fold: finished chunks TMEM -> fp32 sums in shared memory ====================
-        // warp 4: lane m = row m of D (z index k); warp 5: lane 0 = row 32 (the ones row: dL/db)
-        const bool active = (warp == 4) || (lane == 0);
-        const int m = (warp == 4) ? lane : 32;
+        // warp 8: lane m = row m of D (z index k); warp 9: lane 0 = row 32 (the ones row: dL/db)
+        const bool active = (warp == 8) || (lane == 0);
+        const int m = (warp == 8) ? lane : 32;
         for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
             const int set = (int)(chunk & 1);
             if (active) {
@@ -191,22 +197,22 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             }
         }
     } else {
-        // ================================ producers: warp g = hidden units 8g .. 8g+7, lane = pair =====================
-        const int g = warp, p = lane;
+        // ================================ producers: warp = (MN block g, half of it), lane = pair =======================
+        const int g = warp & 3, half = warp >> 2, p = lane;
+        const int x = p & 7;                                              // 128-byte swizzle: chunk c of row p sits at c ^ x
         for (int64_t j = 0; j < n_mine; ++j) {
             const int s = (int)(j % kStg), b = (int)(j % kBuf);
             const int64_t item = first + j * stride;
             const int e = (int)(item / n_blocks);
-            const bool live = (item - (int64_t)e * n_blocks) * kPairs + p < n_paths;
             const float we = stage_weight[e], fr = stage_frac[e];
             mbar_wait(&stg_full[s], (uint32_t)((j / kStg) & 1));
             const unsigned char* stg = smem + oStg + s * kStgBytes;
-            const float4 a0 = *reinterpret_cast<const float4*>(stg + p * 128 + g * 32), a1 = *reinterpret_cast<const float4*>(stg + p * 128 + g * 32 + 16);
-            const float4 z0 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + g * 32), z1 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + g * 32 + 16);
+            // a[8g + 4 half .. +4) and z likewise: chunk 2g + half of the pair's row
+            const float4 a0 = *reinterpret_cast<const float4*>(stg + p * 128 + (((2 * g + half) ^ x) << 4));
+            const float4 z0 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + (((2 * g + half) ^ x) << 4));
             float dx[8];
             if (cubic) {
-                const unsigned char* row = stg + 8192 + p * 128;          // [a | b | 2c | 3d], chunk c at position c ^ (p & 7)
-                const int x = p & 7;
+                const unsigned char* row = stg + 8192 + p * 128;          // [a | b | 2c | 3d]
                 const float4 b0 = *reinterpret_cast<const float4*>(row + ((2 ^ x) << 4)), b1 = *reinterpret_cast<const float4*>(row + ((3 ^ x) << 4));
                 const float4 c0 = *reinterpret_cast<const float4*>(row + ((4 ^ x) << 4)), c1 = *reinterpret_cast<const float4*>(row + ((5 ^ x) << 4));
                 const float4 d0 = *reinterpret_cast<const float4*>(row + ((6 ^ x) << 4)), d1 = *reinterpret_cast<const float4*>(row + ((7 ^ x) << 4));
@@ -223,31 +229,27 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 for (int c = 0; c < C; ++c) dx[c] = bb[c] * we;
             }
             mbar_arrive(&stg_free[s]);                                    // staging read into registers: the TMA warp may refill it
-            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-            if (!live) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { av[i] = 0.f; zv[i] = 0.f; }
-            }
+            const float av[4] = {a0.x, a0.y, a0.z, a0.w};                 // rows beyond n_paths arrived as zeros
             mbar_wait(&empty[b], (uint32_t)(((j / kBuf) & 1) ^ 1));       // the MMAs that last read this buffer are done
             unsigned char* buf = smem + b * kBufBytes;
             // U[pair][n = (8g + hh) * 8 + c] = a[hh] * dx[c]: one 16-byte chunk per hidden unit, MN block g, chunk hh
 #pragma unroll
-            for (int hh = 0; hh < 8; ++hh) {
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int hh = 4 * half + q4;
                 uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) split_bf2(av[hh] * dx[2 * q], av[hh] * dx[2 * q + 1], hi[q], lo[q]);
+                for (int q = 0; q < 4; ++q) split_bf2(av[q4] * dx[2 * q], av[q4] * dx[2 * q + 1], hi[q], lo[q]);
                 const uint32_t off = mn_off(g, p, hh);
                 *reinterpret_cast<uint4*>(buf + oA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(buf + oA + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            {   // Zx[pair][m = 8g .. 8g+7] = z: chunk g of MN block 0
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) split_bf2(zv[2 * q], zv[2 * q + 1], hi[q], lo[q]);
-                const uint32_t off = mn_off(0, p, g);
-                *reinterpret_cast<uint4*>(buf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(buf + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            {   // Zx[pair][m = 8g + 4 half .. +4) = z: half of chunk g of MN block 0
+                uint32_t hi[2], lo[2];
+                split_bf2(z0.x, z0.y, hi[0], lo[0]);
+                split_bf2(z0.z, z0.w, hi[1], lo[1]);
+                const uint32_t off = mn_off(0, p, g) + 8 * half;
+                *reinterpret_cast<uint2*>(buf + off) = make_uint2(hi[0], hi[1]);
+                *reinterpret_cast<uint2*>(buf + 8192 + off) = make_uint2(lo[0], lo[1]);
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -264,7 +266,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         mine[e] = acc[n * 33 + k];
     }
     for (int n = tid; n < kN; n += kThreads) mine[H * C * H + n] = acc[n * 33 + 32];
-    if (warp == 6) tmem_dealloc(tmem_base, 512);
+    if (warp == 10) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace pg2
@@ -286,8 +288,13 @@ int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, 
     const int row_floats = (control_kind == TCDE_CONTROL_CUBIC) ? 4 * pg2::C : pg2::C;
     const int rc = tc::make_rows_tensor_map(&rows_map, control, n_paths, n_rows, row_floats, pg2::kPairs);
     TCDE_CHECK_SUPPORTED(rc == 0, "parameter gradients: cuTensorMapEncodeTiled failed (%d)", rc);
+    alignas(64) CUtensorMap a_map, z_map;
+    const int rca = tc::make_stage_tensor_map(&a_map, const_cast<float*>(a_stages), n_paths, n_stage_total, pg2::kPairs);
+    const int rcz = tc::make_stage_tensor_map(&z_map, const_cast<float*>(z_stages), n_paths, n_stage_total, pg2::kPairs);
+    TCDE_CHECK_SUPPORTED(rca == 0 && rcz == 0, "parameter gradients: cuTensorMapEncodeTiled failed (%d, %d) for the stage trajectories", rca, rcz);
     pg2::param_grad_bf16_kernel<<<grid, pg2::kThreads, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index,
-                                                                      stage_frac, stage_weight, n_stage_total, scratch, n_paths, rows_map);
+                                                                      stage_frac, stage_weight, n_stage_total, scratch, n_paths, rows_map,
+                                                                      a_map, z_map);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }

@@ -69,6 +69,9 @@ template <int MODE> struct Smem {
     static constexpr int red = a_aug + kTiles * kTile * 32;                          // 64 floats of reduction scratch
     static constexpr int bars = red + 256;                                           // a_ready[2], d_ready[2], raw_full[2][2], tmem slot
     static constexpr int total = bars + 128;
+    // MODE 1 with a stage dump: one [128 rows x 128 B] staging tile per tile (TMA store source, 128-byte swizzle)
+    static constexpr int dump = (total + 1023) & ~1023;
+    static constexpr int total_dump = dump + kTiles * kTile * 128;
 };
 
 __device__ __forceinline__ void reg_dealloc_24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::: "memory"); }
@@ -115,12 +118,17 @@ __device__ __forceinline__ void issue_tile(uint32_t d, unsigned char* smem, unsi
         mma_f16(d, da + 2, db + 2, idesc, 1);
         mma_f16(d, da_aug, db_aug, idesc, 1);                 // + row_scale * bias
     }
-    mma_commit(d_ready);
+    if (d_ready) mma_commit(d_ready);
 }
 
 template <int MODE, bool TRACE, bool DUMP>
-__global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a, const Units un, const __grid_constant__ CUtensorMap rows_map) {
+__global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a, const Units un, const __grid_constant__ CUtensorMap rows_map,
+                                                                const __grid_constant__ CUtensorMap dump_map) {
     using S = Smem<MODE>;
+    // the stage dump of the adjoint goes through a swizzled staging tile and ONE TMA tensor store per tile and stage (MODE 1;
+    // MODE 0 has no shared memory left for it): 32 row threads storing 128 B each straight to HBM touch 32 lines per
+    // instruction -- measured 5.9 ms per dumping solve against 3.0 ms without the dump
+    constexpr bool kStaged = DUMP && MODE == 1;
     using E = exact<float>;
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -235,13 +243,23 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     const bool tr = TRACE && a.trace && u == 0 && t == 0 && st < 64;
                     if (tr) a.trace[st * 8 + 0] = clock64();
                     issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
-                                     smem + S::a_aug + t * kTile * 32, &d_ready[t]);
+                                     smem + S::a_aug + t * kTile * 32, kStaged ? nullptr : &d_ready[t]);
                     if (tr) a.trace[st * 8 + 1] = clock64();
                     ++kcount;
                     // the rows of the NEXT stage: their buffer was last read two stages ago, before the arrivals just waited for
                     if (st + 1 < st_hi) fetch_rows(kcount, idx_fetch);
+                    if (kStaged) {
+                        // this stage's input rows (staged by the row threads before their arrival) -> the trajectory in HBM.
+                        // The commit that releases the row threads into the next stage is issued once the TMA unit has READ
+                        // the staging tile -- long before the 7 MMAs above have finished, so nobody waits for it
+                        tma_store_3d(&dump_map, smem + S::dump + t * kTile * 128, 0, (int)tile_path0, st);
+                        bulk_commit();
+                        bulk_wait_read<0>();
+                        mma_commit(&d_ready[t]);
+                    }
                 }
             }
+            if (kStaged && (tid & 31) == 0) bulk_wait_all();  // the unit's trajectory rows are in HBM before the unit is released
             __syncwarp();                                     // lanes 1-31 wait here for lane 0: the CTA barriers below are warp-aligned
             TCDE_UNIT_EPILOGUE()
         }
@@ -262,7 +280,12 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
             float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
 
             auto write_a = [&](const float* z, int stage_no) {   // next stage input -> split operand rows
-                if (DUMP && live) {                       // ... and, for the adjoint, to the trajectory in HBM
+                if (kStaged) {                            // ... and, for the adjoint, to the trajectory in HBM (via the staging tile)
+                    unsigned char* row = smem + S::dump + t * kTile * 128 + r * 128;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *reinterpret_cast<float4*>(row + ((c4 ^ (r & 7)) << 4)) = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
+                } else if (DUMP && live) {
                     float4* dst = reinterpret_cast<float4*>(a.stage_dump + ((int64_t)stage_no * a.n_paths + path) * kH);
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
@@ -499,7 +522,8 @@ template <int MODE> static int launch_tc(const UmmaArgs& a, cudaStream_t stream)
     const int grid = (int)(n_units < sms ? n_units : sms);
     auto kern = a.stage_dump ? tc::cdeint_tc_kernel<MODE, false, true>
                              : a.trace ? tc::cdeint_tc_kernel<MODE, true, false> : tc::cdeint_tc_kernel<MODE, false, false>;
-    constexpr int smem = tc::Smem<MODE>::total + 1024;      // slack for the 1024-byte alignment of the tiles
+    const bool staged = a.stage_dump != nullptr && MODE == 1;
+    const int smem = (staged ? tc::Smem<MODE>::total_dump : tc::Smem<MODE>::total) + 1024;   // slack for the 1024-byte alignment of the tiles
     TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     alignas(64) CUtensorMap rows_map;
     const int row_floats = (a.control_kind == TCDE_CONTROL_CUBIC) ? 4 * tc::kC : tc::kC;
@@ -523,7 +547,12 @@ template <int MODE> static int launch_tc(const UmmaArgs& a, cudaStream_t stream)
         TCDE_CHECK_CUDA(cudaMemsetAsync(un.progress, 0, flag_bytes, stream));
         tc::segment_cursor_kernel<<<1, 32, 0, stream>>>(a.out_step, a.n_out, n_seg, steps_per_seg, cursor);
     }
-    kern<<<grid, tc::kThreads, smem, stream>>>(a, un, rows_map);
+    alignas(64) CUtensorMap dump_map = rows_map;            // only read by the dumping MODE 1 kernel
+    if (staged) {
+        const int rc2 = tc::make_stage_tensor_map(&dump_map, a.stage_dump, a.n_paths, (int64_t)a.n_steps * a.n_stages);
+        TCDE_CHECK_SUPPORTED(rc2 == 0, "tensor-core solve: cuTensorMapEncodeTiled failed (%d) for the stage trajectory", rc2);
+    }
+    kern<<<grid, tc::kThreads, smem, stream>>>(a, un, rows_map, dump_map);
     const cudaError_t launch_err = cudaGetLastError();
     if (workspace) cudaFreeAsync(workspace, stream);
     TCDE_CHECK_CUDA(launch_err);
