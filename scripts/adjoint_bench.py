@@ -18,7 +18,7 @@ L, C, H = 256, 8, 32
 dev = torch.device("cuda")
 
 
-def run(batch, fused, method="rk4", reps=2):
+def run(batch, fused, method="rk4", reps=int(os.environ.get("TCDE_REPS", "2"))):
     gen = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(batch, L, C, generator=gen, device=dev).cumsum(1) / math.sqrt(L)
     z0 = torch.randn(batch, H, generator=gen, device=dev)
@@ -42,6 +42,9 @@ def run(batch, fused, method="rk4", reps=2):
             out[:, -1].sum().backward()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            if os.environ.get("TCDE_VERBOSE"):
+                st = torch.cuda.memory_stats()
+                print("rep: {:.4f} s  cudaMalloc calls so far {}  retries {}".format(dt, st.get("num_device_alloc", -1), st.get("num_alloc_retries", -1)), flush=True)
             best = dt if best is None else min(best, dt)
         return {"batch": batch, "fused_stage": fused, "method": method, "seconds_fwd_bwd": best,
                 "sequences_per_s": batch / best, "grad_weight_norm": float(func.linear.weight.grad.norm())}

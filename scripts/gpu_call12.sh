@@ -2,6 +2,8 @@
 # round 2, call 12: the two-threads-per-path solve kernel (variant 5): parity, trace, timing; mask-based gap fill: parity + timing
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
+TCDE_VERBOSE=1 TCDE_REPS=6 timeout 300 python scripts/adjoint_bench.py 65536 0 > gpurun_out/r02_adjoint_bench4.txt 2>&1
+cat gpurun_out/r02_adjoint_bench4.txt
 timeout 900 python -m pytest tests/test_gpu_solve.py tests/test_gpu_builders.py tests/test_gpu_round2.py -q -x -k "variant or fill or linear or hermite or fused" > gpurun_out/r02_tests_c12.txt 2>&1
 tail -6 gpurun_out/r02_tests_c12.txt
 timeout 300 python scripts/trace_tc.py 5,4 0,5,85,1029 > gpurun_out/r02_trace_tc2k.txt 2>&1

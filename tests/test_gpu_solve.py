@@ -256,12 +256,12 @@ def _set_variant(v):
     _lib.call("tcde_set_solve_variant", v)
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 32, 5, 5 + 16 * 32])
+@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 32, 4 + 16 * 2])
 @pytest.mark.parametrize("batch", [1, 100, 128, 129, 256, 300, 1000])
 def test_tensor_core_variant_matches_cuda_core_and_oracle(batch, variant):
     """The tcgen05 kernels -- 2: solve_umma.cu (round 1, 3xTF32), 3 / 4: solve_tc.cu (Runge-Kutta state in registers;
     3xTF32 / 2xFP16 with per-path power-of-two scaling; + 16 * 32: the time axis forced into four segments handed over
-    through HBM) -- against solve_simt.cu and the fp64 oracle, including partial tiles (batch not a multiple of 128 / 256)."""
+    through HBM; + 16 * 2: the proxy fence in every row thread as well as in the issuer) -- against solve_simt.cu and the fp64 oracle, including partial tiles (batch not a multiple of 128 / 256)."""
     length, channels, hidden = 40, 8, 32
     gen = torch.Generator().manual_seed(batch)
     x = torch.randn(batch, length, channels, generator=gen, dtype=torch.float64).cumsum(1) / math.sqrt(length)
@@ -294,7 +294,7 @@ def test_tensor_core_variant_matches_cuda_core_and_oracle(batch, variant):
         _set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 16, 5])
+@pytest.mark.parametrize("variant", [2, 3, 4, 4 + 16 * 16, 4 + 16 * 2])
 def test_tensor_core_variant_full_size(variant):
     gen = torch.Generator(device=DEV).manual_seed(0)
     B, L, C, H = 65536, 256, 8, 32
@@ -321,7 +321,7 @@ def test_tensor_core_variant_full_size(variant):
         _set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 4 + 16 * 32, 5, 5 + 16 * 32])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 4 + 16 * 32])
 def test_decreasing_output_times(variant):
     """A decreasing t is integrated as -t with the field negated (torchdiffeq's time reversal)."""
     length, channels, hidden, batch = 20, 8, 32, 70

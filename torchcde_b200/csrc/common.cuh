@@ -109,16 +109,14 @@ struct UmmaArgs {
     float sign;
     long long* trace;     // optional [64][8] clock64 stamps of CTA 0 / tile 0 (profiling aid), else nullptr
     float* stage_dump;    // optional [n_steps * n_stages][n_paths][32]: the input of every stage (for the adjoint)
-    int debug;            // solve_tc.cu: profiling experiments with WRONG results (1 no row fetch, 2 no proxy fence, 4 no TMEM reads,
-                          // 8 no split) and scheduling switches with right results (16 one segment, 32 force four segments)
+    int debug;            // solve_tc.cu: profiling experiments with WRONG results (1 no row fetch, 4 no TMEM reads,
+                          // 8 no split) and switches with right results (2 proxy fence in every row thread too, 16 one segment, 32 force four segments, 64 no stagger)
 };
 bool solve_umma_supported(int H, int C);
 int solve_umma_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
 // round-2 kernel (solve_tc.cu): Runge-Kutta state in registers; mode 0 = 3xTF32 (13 MMAs per stage), mode 1 = 2xFP16 with
 // per-path power-of-two scaling (7 MMAs per stage)
 int solve_tc_f32(const UmmaArgs& a, int H, int C, int mode, cudaStream_t stream);
-// solve_tc2.cu: mode 1 with two threads per path (each owns half of the hidden state); no stage dump
-int solve_tc2_f32(const UmmaArgs& a, int H, int C, cudaStream_t stream);
 int current_solve_variant();          // tcde_set_solve_variant: 0 auto, 1 CUDA-core, 2 tcgen05 round 1, 3 tcgen05 TF32 r2, 4 tcgen05 FP16 r2
 
 // parameter gradients of a whole backward solve on the tensor cores (param_grad_umma.cu)

@@ -327,88 +327,6 @@ __device__ __forceinline__ bool fill_tile_in_place(T* tile, const T* ts, int L, 
     return head >= 0;
 }
 
-// The same fill for chunks of at most 64 positions (every shape up to length 64 x (32 / channels), the BASELINE shapes
-// included): the holes of a lane's chunk are ONE 64-bit mask, built in a single pass (load, compare, set a bit), and
-// everything the list version above finds by walking -- the first / last observation of the chunk, whether a hole opens
-// a gap, where the gap ends -- is a count-trailing-zeros on that mask.  ncu on the list version at the benchmark shape:
-// 3,906 warp-instructions per path, 1,600 of them in the backward walk that threads the list (23 per position with the
-// divergent hole / observation branches); the mask pass is ~3 per position.
-template <typename T, bool UNIT>
-__device__ __forceinline__ bool fill_tile_masks(T* tile, const T* ts, int L, int C, int lgG, int padw, int lane) {
-    using E = exact<T>;
-    const int G = 1 << lgG;
-    const int nch = (L + G - 1) >> lgG;
-    const int c = lane % C, j = lane / C;
-    const bool active = j < nch;
-    const int g0 = j << lgG, g1 = min(g0 + G, L), n = active ? g1 - g0 : 0;
-    const unsigned full = 0xffffffffu;
-    auto word = [&](int i) { return i * C + (i >> lgG) * padw; };
-    auto time_of = [&](int i) -> T { return UNIT ? T(i) : ts[i]; };
-    T* base = tile + word(active ? g0 : 0) + c;             // a chunk has no padding inside: position g0 + k at base[k * C]
-    unsigned long long m = 0;
-#pragma unroll 8
-    for (int k = 0; k < n; ++k)
-        if (is_nan(base[k * C])) m |= 1ull << k;
-    const unsigned long long valid = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-    const unsigned long long obs = ~m & valid;
-    int first_idx = kFillNone, last_idx = -1;
-    T last_val = T(0);
-    if (obs) {
-        first_idx = g0 + (__ffsll((long long)obs) - 1);
-        const int last_rel = 63 - __clzll((long long)obs);
-        last_idx = g0 + last_rel;
-        last_val = base[last_rel * C];
-    }
-    // nearest observation in the chunks after (position) and before (position, value) this one
-    int after = kFillNone, before = -1;
-    T before_val = T(0);
-    for (int d = 1; d < nch; ++d) {
-        const int fa = __shfl_down_sync(full, first_idx, C * d);
-        const int la = __shfl_up_sync(full, last_idx, C * d);
-        const T lv = __shfl_up_sync(full, last_val, C * d);
-        if (after == kFillNone && j + d < nch) after = fa;
-        if (before < 0 && j - d >= 0) { before = la; before_val = lv; }
-    }
-    const int series_first = __shfl_sync(full, first_idx != kFillNone ? first_idx : after, c);
-    const int series_last = __shfl_sync(full, last_idx >= 0 ? last_idx : before, c + C * (nch - 1));
-    if (active && m) {
-        if (series_first == kFillNone) {                    // nothing observed: the zero path (linear.py:19-21)
-            for (int k = 0; k < n; ++k) base[k * C] = T(0);
-        } else {
-            const T v_first = tile[word(series_first) + c], v_last = tile[word(series_last) + c];
-            // the ends of the series count as observations carrying the first / last value (linear.py:31-34)
-            int prev_idx = before >= 0 ? before : 0;
-            T prev_val = before >= 0 ? before_val : v_first;
-            const int far_idx = after != kFillNone ? after : L - 1;
-            const T far_val = after != kFillNone ? tile[word(after) + c] : v_last;
-            T lo_t = T(0), span = T(1), rise = T(0);
-            for (unsigned long long mm = m; mm; mm &= mm - 1ull) {
-                const int k = __ffsll((long long)mm) - 1;
-                if (k == 0 || !((m >> (k - 1)) & 1ull)) {   // this hole opens a gap: fetch the gap's end points
-                    if (k > 0) {
-                        prev_idx = g0 + k - 1;
-                        prev_val = base[(k - 1) * C];
-                    }
-                    const unsigned long long rest = ~(m >> k);                      // zero only for k = 0 and 64 holes
-                    const int hk = rest ? k + (__ffsll((long long)rest) - 1) : 64;  // first position after the run of holes
-                    const bool inside = hk < n;
-                    const int hi_i = inside ? g0 + hk : far_idx;
-                    const T hi_v = inside ? base[hk * C] : far_val;
-                    lo_t = time_of(prev_idx);
-                    span = E::sub(time_of(hi_i), lo_t);
-                    rise = E::sub(hi_v, prev_val);
-                }
-                // linear.py:60-69: x[j] = lo + ((t_j - t_lo) / (t_hi - t_lo)) * (hi - lo)
-                base[k * C] = E::add(prev_val, E::mul(E::div(E::sub(time_of(g0 + k), lo_t), span), rise));
-            }
-            // an imputed end point is a copy of the observation, not an interpolation
-            if (g0 == 0 && series_first > 0) tile[c] = v_first;
-            if (g1 == L && series_last < L - 1) tile[word(L - 1) + c] = v_last;
-        }
-    }
-    return m != 0;
-}
-
 // OUT = 0: the filled series (linear_interpolation_coeffs).  OUT = 1: the Hermite coefficients with backward
 // differences of the filled series (interpolation_hermite_cubic_bdiff.py:23-44 = fill, then :8-20) straight from the
 // warp's tile -- one launch, the filled series never goes to HBM, and no NaN flag has to travel to the host to decide
@@ -468,8 +386,7 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
         __syncwarp();
         if (__any_sync(full, hole)) {
             saw_nan = true;
-            if (lgG <= 6) fill_tile_masks<T, UNIT>(tile, ts, L, C, lgG, padw, lane);
-            else fill_tile_in_place<T, UNIT>(tile, ts, L, C, lgG, padw, lane);
+            fill_tile_in_place<T, UNIT>(tile, ts, L, C, lgG, padw, lane);
             __syncwarp();
         }
         if (OUT == 0) {

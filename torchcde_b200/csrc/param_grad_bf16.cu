@@ -15,8 +15,10 @@
 //     needs no more, and unlike FP16 no scaling is needed: a per-pair scale cannot be factored out of a sum over pairs);
 //   * a, z and the spline rows of an item arrive by TMA (three tensor boxes of 32 paths, 128-byte swizzle: the producers'
 //     128-bit reads of their own row are bank-conflict free -- linear rows cost 8 wavefronts per load, ncu: 58 % LSU) into
-//     a 3-deep staging ring; the eight producer warps share an item (warp = MN block g of U = hidden units 8g..8g+7,
-//     half of it: four 16-byte chunks).  Four producer warps needed ~1,900 cycles per item against 768 of tensor pipe.
+//     a 3-deep staging ring; the sixteen producer warps share an item (warp = MN block g of U = hidden units 8g..8g+7,
+//     a quarter of it: two 16-byte chunks).  An item is a serial chain per warp (barrier wait, loads, products, stores,
+//     proxy fence, arrive) -- four producer warps needed ~1,900 cycles per item, eight 1,390, against 768 of tensor pipe:
+//     more warps per scheduler hide that chain.
 // The tensor core adds into its fp32 accumulator with truncation (measured in round 1: 2.6e-3 relative drift over ~10^5
 // accumulations), so accumulation runs in chunks of kChunk items into two alternating TMEM sets; two fold warps add each
 // finished chunk into fp32 sums in shared memory with round-to-nearest adds, one chunk behind the tensor pipe.
@@ -32,8 +34,8 @@ using namespace umma;
 constexpr int H = 32, C = 8;
 constexpr int kPairs = 32;                 // (stage, path) pairs per item == K of one operand buffer
 constexpr int kN = 256, kM = 128;
-constexpr int kProducers = 256;            // threads of warps 0-7
-constexpr int kThreads = 384;              // warps 0-7 producers, 8-9 fold, 10 MMA issuer, 11 TMA
+constexpr int kProducers = 512;            // threads of warps 0-15
+constexpr int kThreads = 640;              // warps 0-15 producers, 16-17 fold, 18 MMA issuer, 19 TMA
 constexpr int kBuf = 3, kStg = 3, kChunk = 16;
 constexpr int kParams = H * C * H + H * C;
 
@@ -111,7 +113,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         tc::tma_prefetch_desc(&a_map);
         tc::tma_prefetch_desc(&z_map);
     }
-    if (warp == 10) tmem_alloc(tmem_slot, 512);
+    if (warp == 18) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -124,7 +126,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
     const int64_t n_mine = first < n_items ? (n_items - first + stride - 1) / stride : 0;
     const int64_t n_chunks = (n_mine + kChunk - 1) / kChunk;
 
-    if (warp == 11) {
+    if (warp == 19) {
         // ================================ TMA: a, z, spline rows of item j -> staging ================================
         if (lane == 0) {
             for (int64_t j = 0; j < n_mine; ++j) {
@@ -141,7 +143,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 tc::tma_load_2d(dst + 8192, &rows_map, stage_index[e] * row_floats, (int)path0, &stg_full[s]);
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 18) {
         // ================================ MMA issuer ===================================================================
         if (lane == 0) {
             // D = F32, A = B = BF16, both MN-major, N = 256, M = 128
@@ -153,6 +155,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 const bool opens = (j % kChunk) == 0, closes = (j % kChunk) == kChunk - 1 || j == n_mine - 1;
                 if (opens && chunk >= 2) mbar_wait(&set_free[set], (uint32_t)(((chunk >> 1) & 1) ^ 1));     // chunk - 2 has been folded
                 mbar_wait(&full[b], (uint32_t)((j / kBuf) & 1));
+                fence_proxy_async_smem();                                 // the producers' generic-proxy stores -> async proxy
                 tc_fence_after();
                 unsigned char* buf = smem + b * kBufBytes;
                 const uint32_t d = tmem_base + (uint32_t)(set * kN);
@@ -168,11 +171,11 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 if (closes) mma_commit(&chunk_done[set]);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 16) {
         // ================================ fold: finished chunks TMEM -> fp32 sums in shared memory ====================
-        // warp 8: lane m = row m of D (z index k); warp 9: lane 0 = row 32 (the ones row: dL/db)
-        const bool active = (warp == 8) || (lane == 0);
-        const int m = (warp == 8) ? lane : 32;
+        // warp 16: lane m = row m of D (z index k); warp 17: lane 0 = row 32 (the ones row: dL/db)
+        const bool active = (warp == 16) || (lane == 0);
+        const int m = (warp == 16) ? lane : 32;
         for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
             const int set = (int)(chunk & 1);
             if (active) {
@@ -197,8 +200,8 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             }
         }
     } else {
-        // ================================ producers: warp = (MN block g, half of it), lane = pair =======================
-        const int g = warp & 3, half = warp >> 2, p = lane;
+        // ================================ producers: warp = (MN block g, quarter of it), lane = pair ====================
+        const int g = warp & 3, qt = warp >> 2, p = lane;
         const int x = p & 7;                                              // 128-byte swizzle: chunk c of row p sits at c ^ x
         for (int64_t j = 0; j < n_mine; ++j) {
             const int s = (int)(j % kStg), b = (int)(j % kBuf);
@@ -207,9 +210,10 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             const float we = stage_weight[e], fr = stage_frac[e];
             mbar_wait(&stg_full[s], (uint32_t)((j / kStg) & 1));
             const unsigned char* stg = smem + oStg + s * kStgBytes;
-            // a[8g + 4 half .. +4) and z likewise: chunk 2g + half of the pair's row
-            const float4 a0 = *reinterpret_cast<const float4*>(stg + p * 128 + (((2 * g + half) ^ x) << 4));
-            const float4 z0 = *reinterpret_cast<const float4*>(stg + 4096 + p * 128 + (((2 * g + half) ^ x) << 4));
+            // a[8g + 2 qt .. +2) and z likewise: 8 bytes of chunk 2g + (qt >> 1) of the pair's row
+            const uint32_t az_off = (uint32_t)(p * 128 + (((2 * g + (qt >> 1)) ^ x) << 4) + 8 * (qt & 1));
+            const float2 a0 = *reinterpret_cast<const float2*>(stg + az_off);
+            const float2 z0 = *reinterpret_cast<const float2*>(stg + 4096 + az_off);
             float dx[8];
             if (cubic) {
                 const unsigned char* row = stg + 8192 + p * 128;          // [a | b | 2c | 3d]
@@ -229,30 +233,28 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 for (int c = 0; c < C; ++c) dx[c] = bb[c] * we;
             }
             mbar_arrive(&stg_free[s]);                                    // staging read into registers: the TMA warp may refill it
-            const float av[4] = {a0.x, a0.y, a0.z, a0.w};                 // rows beyond n_paths arrived as zeros
+            const float av[2] = {a0.x, a0.y};                             // rows beyond n_paths arrived as zeros
             mbar_wait(&empty[b], (uint32_t)(((j / kBuf) & 1) ^ 1));       // the MMAs that last read this buffer are done
             unsigned char* buf = smem + b * kBufBytes;
             // U[pair][n = (8g + hh) * 8 + c] = a[hh] * dx[c]: one 16-byte chunk per hidden unit, MN block g, chunk hh
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const int hh = 4 * half + q4;
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const int hh = 2 * qt + q2;
                 uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) split_bf2(av[q4] * dx[2 * q], av[q4] * dx[2 * q + 1], hi[q], lo[q]);
+                for (int q = 0; q < 4; ++q) split_bf2(av[q2] * dx[2 * q], av[q2] * dx[2 * q + 1], hi[q], lo[q]);
                 const uint32_t off = mn_off(g, p, hh);
                 *reinterpret_cast<uint4*>(buf + oA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(buf + oA + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            {   // Zx[pair][m = 8g + 4 half .. +4) = z: half of chunk g of MN block 0
-                uint32_t hi[2], lo[2];
-                split_bf2(z0.x, z0.y, hi[0], lo[0]);
-                split_bf2(z0.z, z0.w, hi[1], lo[1]);
-                const uint32_t off = mn_off(0, p, g) + 8 * half;
-                *reinterpret_cast<uint2*>(buf + off) = make_uint2(hi[0], hi[1]);
-                *reinterpret_cast<uint2*>(buf + 8192 + off) = make_uint2(lo[0], lo[1]);
+            {   // Zx[pair][m = 8g + 2 qt .. +2) = z: a quarter of chunk g of MN block 0
+                uint32_t hi, lo;
+                split_bf2(z0.x, z0.y, hi, lo);
+                const uint32_t off = mn_off(0, p, g) + 4 * qt;
+                *reinterpret_cast<uint32_t*>(buf + off) = hi;
+                *reinterpret_cast<uint32_t*>(buf + 8192 + off) = lo;
             }
-            fence_proxy_async_smem();
-            tc_fence_before();
+            tc_fence_before();                                            // the issuer runs the proxy fence after its acquire
             mbar_arrive(&full[b]);
         }
     }
@@ -266,7 +268,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         mine[e] = acc[n * 33 + k];
     }
     for (int n = tid; n < kN; n += kThreads) mine[H * C * H + n] = acc[n * 33 + 32];
-    if (warp == 10) tmem_dealloc(tmem_base, 512);
+    if (warp == 18) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace pg2

@@ -577,8 +577,6 @@ static int solve_fixed_linear(const void* control, int control_kind, int64_t n_r
                        (int)n_out, (float)sign, g_trace, (float*)stage_dump, g_debug_flags};
             if (g_solve_variant == 2) return solve_umma_f32(u, (int)hidden, (int)channels, s);        // the round-1 kernel, kept for comparison
             // round-2 kernel: 3 / 6 = 3xTF32 split, 4 / 5 = 2xFP16 split (5, 6: aliases from the development history)
-            // 5 = the two-threads-per-path kernel (solve_tc2.cu; no stage dump: the adjoint's dumping solves use variant 4's kernel)
-            if (g_solve_variant == 5 && stage_dump == nullptr) return solve_tc2_f32(u, (int)hidden, (int)channels, s);
             const int mode = (g_solve_variant == 3 || g_solve_variant == 6) ? 0 : (g_solve_variant == 4 || g_solve_variant == 5) ? 1
                                                                                                                                   : TCDE_DEFAULT_TC_MODE;
             return solve_tc_f32(u, (int)hidden, (int)channels, mode, s);

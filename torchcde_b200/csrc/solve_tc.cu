@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     if (st + 2 < st_hi) idx_next = a.stage_index[st + 2];
                     mbar_wait(&a_ready[t], phase_a);
                     phase_a ^= 1;
+                    fence_proxy_async_smem();                 // the row threads' operand (and staging) stores -> async proxy
                     tc_fence_after();
                     const bool tr = TRACE && a.trace && u == 0 && t == 0 && st < 64;
                     if (tr) a.trace[st * 8 + 0] = clock64();
@@ -307,7 +308,11 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                 } else if (!(a.debug & 8)) {
                     inv_scale = split_store_fp16(z, a_tile, a_aug, r, beta, inv_w_scale);
                 }
-                if (!(a.debug & 2)) fence_proxy_async_smem();
+                // no proxy fence here: the arrival (release) publishes these generic-proxy stores to the issuer thread, which
+                // executes ONE fence.proxy.async after its acquire and before it hands the rows to the tensor core / TMA unit.
+                // A fence per row thread (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) sat on the critical chain: ~330 cycles per stage
+                // (debug bit 1 (2): put it back, for A/B timing)
+                if (a.debug & 2) fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(&a_ready[t]);
             };
