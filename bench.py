@@ -564,7 +564,7 @@ def run_gpu_arm(args):
         "gpu_launches": args.steps,
         "roofline": ({
             "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2165000000, "peak_source": peaks["source"],
+            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2228860000, "peak_source": peaks["source"],
             "kernel": kernel_name,
             "algorithmic_flops_per_launch": BATCH * FLOPS_PER_SEQ,
             "note": "achieved = ALGORITHMIC flops (17.6 MFLOP/seq) / time against the measured dense bf16 peak, as the "

@@ -25,6 +25,7 @@
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace tcde {
 namespace pg2 {
@@ -34,8 +35,8 @@ using namespace umma;
 constexpr int H = 32, C = 8;
 constexpr int kPairs = 32;                 // (stage, path) pairs per item == K of one operand buffer
 constexpr int kN = 256, kM = 128;
-constexpr int kProducers = 512;            // threads of warps 0-15
-constexpr int kThreads = 640;              // warps 0-15 producers, 16-17 fold, 18 MMA issuer, 19 TMA
+// template parameter Q: parts an MN block of U is cut in = producer warps / 4 (2: warps 0-7, four hidden units per thread;
+// 4: warps 0-15, two per thread); then two fold warps, the MMA issuer warp, the TMA warp
 constexpr int kBuf = 3, kStg = 3, kChunk = 16;
 constexpr int kParams = H * C * H + H * C;
 
@@ -77,12 +78,16 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem, uint
                  : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int Q>
+__global__ void __launch_bounds__(128 * Q + 128, 1)
 param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ z_stages,
                        const float* __restrict__ a_stages, const int32_t* __restrict__ stage_index, const float* __restrict__ stage_frac,
                        const float* __restrict__ stage_weight, int n_stage_total, float* __restrict__ scratch, int64_t n_paths,
                        const __grid_constant__ CUtensorMap rows_map, const __grid_constant__ CUtensorMap a_map,
-                       const __grid_constant__ CUtensorMap z_map) {
+                       const __grid_constant__ CUtensorMap z_map, const int issuer_fence) {
+    constexpr int kProducers = 128 * Q, kThreads = kProducers + 128;
+    constexpr int kFoldWarp = 4 * Q, kIssuerWarp = 4 * Q + 2, kTmaWarp = 4 * Q + 3;
+    constexpr int HU = 8 / Q;                                             // hidden units (16-byte chunks of U) per producer thread
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem + oBars);      // [kStg]
@@ -113,7 +118,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         tc::tma_prefetch_desc(&a_map);
         tc::tma_prefetch_desc(&z_map);
     }
-    if (warp == 18) tmem_alloc(tmem_slot, 512);
+    if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -126,7 +131,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
     const int64_t n_mine = first < n_items ? (n_items - first + stride - 1) / stride : 0;
     const int64_t n_chunks = (n_mine + kChunk - 1) / kChunk;
 
-    if (warp == 19) {
+    if (warp == kTmaWarp) {
         // ================================ TMA: a, z, spline rows of item j -> staging ================================
         if (lane == 0) {
             for (int64_t j = 0; j < n_mine; ++j) {
@@ -143,7 +148,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 tc::tma_load_2d(dst + 8192, &rows_map, stage_index[e] * row_floats, (int)path0, &stg_full[s]);
             }
         }
-    } else if (warp == 18) {
+    } else if (warp == kIssuerWarp) {
         // ================================ MMA issuer ===================================================================
         if (lane == 0) {
             // D = F32, A = B = BF16, both MN-major, N = 256, M = 128
@@ -155,7 +160,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 const bool opens = (j % kChunk) == 0, closes = (j % kChunk) == kChunk - 1 || j == n_mine - 1;
                 if (opens && chunk >= 2) mbar_wait(&set_free[set], (uint32_t)(((chunk >> 1) & 1) ^ 1));     // chunk - 2 has been folded
                 mbar_wait(&full[b], (uint32_t)((j / kBuf) & 1));
-                fence_proxy_async_smem();                                 // the producers' generic-proxy stores -> async proxy
+                if (issuer_fence) fence_proxy_async_smem();               // experiment: one fence here instead of one per producer
                 tc_fence_after();
                 unsigned char* buf = smem + b * kBufBytes;
                 const uint32_t d = tmem_base + (uint32_t)(set * kN);
@@ -171,11 +176,11 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 if (closes) mma_commit(&chunk_done[set]);
             }
         }
-    } else if (warp >= 16) {
+    } else if (warp >= kFoldWarp) {
         // ================================ fold: finished chunks TMEM -> fp32 sums in shared memory ====================
-        // warp 16: lane m = row m of D (z index k); warp 17: lane 0 = row 32 (the ones row: dL/db)
-        const bool active = (warp == 16) || (lane == 0);
-        const int m = (warp == 16) ? lane : 32;
+        // first fold warp: lane m = row m of D (z index k); second: lane 0 = row 32 (the ones row: dL/db)
+        const bool active = (warp == kFoldWarp) || (lane == 0);
+        const int m = (warp == kFoldWarp) ? lane : 32;
         for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
             const int set = (int)(chunk & 1);
             if (active) {
@@ -200,8 +205,8 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             }
         }
     } else {
-        // ================================ producers: warp = (MN block g, quarter of it), lane = pair ====================
-        const int g = warp & 3, qt = warp >> 2, p = lane;
+        // ================================ producers: warp = (MN block g, part of it), lane = pair =======================
+        const int g = warp & 3, part = warp >> 2, p = lane;
         const int x = p & 7;                                              // 128-byte swizzle: chunk c of row p sits at c ^ x
         for (int64_t j = 0; j < n_mine; ++j) {
             const int s = (int)(j % kStg), b = (int)(j % kBuf);
@@ -210,10 +215,18 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             const float we = stage_weight[e], fr = stage_frac[e];
             mbar_wait(&stg_full[s], (uint32_t)((j / kStg) & 1));
             const unsigned char* stg = smem + oStg + s * kStgBytes;
-            // a[8g + 2 qt .. +2) and z likewise: 8 bytes of chunk 2g + (qt >> 1) of the pair's row
-            const uint32_t az_off = (uint32_t)(p * 128 + (((2 * g + (qt >> 1)) ^ x) << 4) + 8 * (qt & 1));
-            const float2 a0 = *reinterpret_cast<const float2*>(stg + az_off);
-            const float2 z0 = *reinterpret_cast<const float2*>(stg + 4096 + az_off);
+            // a[8g + HU part .. + HU) and z likewise: 4 HU bytes of chunk 2g + (HU part) / 4 of the pair's row
+            const uint32_t az_off = (uint32_t)(p * 128 + (((2 * g + (HU * part) / 4) ^ x) << 4) + 4 * ((HU * part) & 3));
+            float av[HU], zv[HU];
+            if (HU == 4) {
+                const float4 a0 = *reinterpret_cast<const float4*>(stg + az_off), z0 = *reinterpret_cast<const float4*>(stg + 4096 + az_off);
+                av[0] = a0.x; av[1] = a0.y; av[HU - 2] = a0.z; av[HU - 1] = a0.w;
+                zv[0] = z0.x; zv[1] = z0.y; zv[HU - 2] = z0.z; zv[HU - 1] = z0.w;
+            } else {
+                const float2 a0 = *reinterpret_cast<const float2*>(stg + az_off), z0 = *reinterpret_cast<const float2*>(stg + 4096 + az_off);
+                av[0] = a0.x; av[1] = a0.y;
+                zv[0] = z0.x; zv[1] = z0.y;
+            }
             float dx[8];
             if (cubic) {
                 const unsigned char* row = stg + 8192 + p * 128;          // [a | b | 2c | 3d]
@@ -233,28 +246,35 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 for (int c = 0; c < C; ++c) dx[c] = bb[c] * we;
             }
             mbar_arrive(&stg_free[s]);                                    // staging read into registers: the TMA warp may refill it
-            const float av[2] = {a0.x, a0.y};                             // rows beyond n_paths arrived as zeros
             mbar_wait(&empty[b], (uint32_t)(((j / kBuf) & 1) ^ 1));       // the MMAs that last read this buffer are done
             unsigned char* buf = smem + b * kBufBytes;
             // U[pair][n = (8g + hh) * 8 + c] = a[hh] * dx[c]: one 16-byte chunk per hidden unit, MN block g, chunk hh
+            // (rows beyond n_paths arrived as zeros)
 #pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-                const int hh = 2 * qt + q2;
+            for (int i = 0; i < HU; ++i) {
+                const int hh = HU * part + i;
                 uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) split_bf2(av[q2] * dx[2 * q], av[q2] * dx[2 * q + 1], hi[q], lo[q]);
+                for (int q = 0; q < 4; ++q) split_bf2(av[i] * dx[2 * q], av[i] * dx[2 * q + 1], hi[q], lo[q]);
                 const uint32_t off = mn_off(g, p, hh);
                 *reinterpret_cast<uint4*>(buf + oA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(buf + oA + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            {   // Zx[pair][m = 8g + 2 qt .. +2) = z: a quarter of chunk g of MN block 0
-                uint32_t hi, lo;
-                split_bf2(z0.x, z0.y, hi, lo);
-                const uint32_t off = mn_off(0, p, g) + 4 * qt;
-                *reinterpret_cast<uint32_t*>(buf + off) = hi;
-                *reinterpret_cast<uint32_t*>(buf + 8192 + off) = lo;
+            {   // Zx[pair][m = 8g + HU part .. + HU) = z: 2 HU bytes of chunk g of MN block 0
+                uint32_t hi[HU / 2], lo[HU / 2];
+#pragma unroll
+                for (int q = 0; q < HU / 2; ++q) split_bf2(zv[2 * q], zv[2 * q + 1], hi[q], lo[q]);
+                const uint32_t off = mn_off(0, p, g) + 2 * HU * part;
+                if (HU == 4) {
+                    *reinterpret_cast<uint2*>(buf + off) = make_uint2(hi[0], hi[HU / 2 - 1]);
+                    *reinterpret_cast<uint2*>(buf + 8192 + off) = make_uint2(lo[0], lo[HU / 2 - 1]);
+                } else {
+                    *reinterpret_cast<uint32_t*>(buf + off) = hi[0];
+                    *reinterpret_cast<uint32_t*>(buf + 8192 + off) = lo[0];
+                }
             }
-            tc_fence_before();                                            // the issuer runs the proxy fence after its acquire
+            if (!issuer_fence) fence_proxy_async_smem();
+            tc_fence_before();
             mbar_arrive(&full[b]);
         }
     }
@@ -268,7 +288,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         mine[e] = acc[n * 33 + k];
     }
     for (int n = tid; n < kN; n += kThreads) mine[H * C * H + n] = acc[n * 33 + 32];
-    if (warp == 18) tmem_dealloc(tmem_base, 512);
+    if (warp == kIssuerWarp) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace pg2
@@ -285,7 +305,8 @@ int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, 
                         const int32_t* stage_index, const float* stage_frac, const float* stage_weight, int n_stage_total,
                         float* scratch, int64_t n_paths, int grid, cudaStream_t stream) {
     constexpr int smem = pg2::kSmem + 1024;                // slack for the 1024-byte alignment of the tiles
-    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     alignas(64) CUtensorMap rows_map;
     const int row_floats = (control_kind == TCDE_CONTROL_CUBIC) ? 4 * pg2::C : pg2::C;
     const int rc = tc::make_rows_tensor_map(&rows_map, control, n_paths, n_rows, row_floats, pg2::kPairs);
@@ -294,9 +315,14 @@ int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, 
     const int rca = tc::make_stage_tensor_map(&a_map, const_cast<float*>(a_stages), n_paths, n_stage_total, pg2::kPairs);
     const int rcz = tc::make_stage_tensor_map(&z_map, const_cast<float*>(z_stages), n_paths, n_stage_total, pg2::kPairs);
     TCDE_CHECK_SUPPORTED(rca == 0 && rcz == 0, "parameter gradients: cuTensorMapEncodeTiled failed (%d, %d) for the stage trajectories", rca, rcz);
-    pg2::param_grad_bf16_kernel<<<grid, pg2::kThreads, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index,
-                                                                      stage_frac, stage_weight, n_stage_total, scratch, n_paths, rows_map,
-                                                                      a_map, z_map);
+    // TCDE_PG_MODE (experiment switch, read once): bit 0 = 16 producer warps instead of 8, bit 1 = proxy fence in the issuer
+    static const int mode = [] { const char* v = getenv("TCDE_PG_MODE"); return v ? atoi(v) : 0; }();
+    if (mode & 1)
+        pg2::param_grad_bf16_kernel<4><<<grid, 640, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index, stage_frac,
+                                                                   stage_weight, n_stage_total, scratch, n_paths, rows_map, a_map, z_map, (mode >> 1) & 1);
+    else
+        pg2::param_grad_bf16_kernel<2><<<grid, 384, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index, stage_frac,
+                                                                   stage_weight, n_stage_total, scratch, n_paths, rows_map, a_map, z_map, (mode >> 1) & 1);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }
