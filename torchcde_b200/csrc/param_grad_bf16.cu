@@ -25,7 +25,6 @@
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
-#include <cstdlib>
 
 namespace tcde {
 namespace pg2 {
@@ -37,17 +36,15 @@ constexpr int kPairs = 32;                 // (stage, path) pairs per item == K 
 constexpr int kN = 256, kM = 128;
 // template parameter Q: parts an MN block of U is cut in = producer warps / 4 (2: warps 0-7, four hidden units per thread;
 // 4: warps 0-15, two per thread); then two fold warps, the MMA issuer warp, the TMA warp
-constexpr int kBuf = 3, kStg = 3, kChunk = 16;
+constexpr int kChunk = 16;
 constexpr int kParams = H * C * H + H * C;
 
 // shared memory map (bytes)
 constexpr int oA = 16384;                                // per buffer: A_hi (8 KB) | A_lo (8 KB) | B_hi (16 KB) | B_lo (16 KB)
 constexpr int kBufBytes = 49152;
-constexpr int oStg = kBuf * kBufBytes;                   // per stage: a (4 KB) | z (4 KB) | rows (4 KB)
-constexpr int kStgBytes = 12288;
-constexpr int oAcc = oStg + kStg * kStgBytes;            // fp32 sums [256 n][33 m]
-constexpr int oBars = oAcc + kN * 33 * 4;
-constexpr int kSmem = oBars + 256;
+constexpr int kStgBytes = 12288;                         // per staging slot: a (4 KB) | z (4 KB) | rows (4 KB)
+// kBuf operand buffers, then kStg staging slots, then the fp32 sums [256 n][33 m], then the mbarriers
+constexpr int smem_bytes(int kBuf, int kStg) { return kBuf * kBufBytes + kStg * kStgBytes + kN * 33 * 4 + 256; }
 
 // byte offset of (pair k, 16-byte chunk `chunk` of MN block `blk`) in an MN-major 128B-swizzled tile with 4 k-groups
 __device__ __forceinline__ uint32_t mn_off(int blk, int k, int chunk) {
@@ -78,7 +75,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem, uint
                  : "memory");
 }
 
-template <int Q>
+template <int Q, int kBuf, int kStg>
 __global__ void __launch_bounds__(128 * Q + 128, 1)
 param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int64_t n_rows, const float* __restrict__ z_stages,
                        const float* __restrict__ a_stages, const int32_t* __restrict__ stage_index, const float* __restrict__ stage_frac,
@@ -88,6 +85,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
     constexpr int kProducers = 128 * Q, kThreads = kProducers + 128;
     constexpr int kFoldWarp = 4 * Q, kIssuerWarp = 4 * Q + 2, kTmaWarp = 4 * Q + 3;
     constexpr int HU = 8 / Q;                                             // hidden units (16-byte chunks of U) per producer thread
+    constexpr int oStg = kBuf * kBufBytes, oAcc = oStg + kStg * kStgBytes, oBars = oAcc + kN * 33 * 4;
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
     uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem + oBars);      // [kStg]
@@ -145,7 +143,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
             int s = 0;
             uint32_t par = 1;                                             // parity of "slot s is free" (free at the start)
             for (int64_t j = 0; j < n_mine; ++j) {
-                mbar_wait(&stg_free[s], par);
+                mbar_wait_relaxed(&stg_free[s], par, 100);
                 const int e = walk_e;
                 const int64_t path0 = (int64_t)walk_blk * kPairs;
                 advance();
@@ -171,7 +169,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
                 const bool opens = (j % kChunk) == 0, closes = (j % kChunk) == kChunk - 1 || j == n_mine - 1;
                 if (opens && chunk >= 2) mbar_wait(&set_free[set], (uint32_t)(((chunk >> 1) & 1) ^ 1));     // chunk - 2 has been folded
                 mbar_wait(&full[b], par);
-                if (issuer_fence) fence_proxy_async_smem();               // experiment: one fence here instead of one per producer
+                if (issuer_fence) fence_proxy_async_smem();               // alternative measured in profiles/r02_pg_modes.txt (off)
                 tc_fence_after();
                 unsigned char* buf = smem + b * kBufBytes;
                 const uint32_t d = tmem_base + (uint32_t)(set * kN);
@@ -196,7 +194,7 @@ param_grad_bf16_kernel(const float* __restrict__ control, int control_kind, int6
         for (int64_t chunk = 0; chunk < n_chunks; ++chunk) {
             const int set = (int)(chunk & 1);
             if (active) {
-                mbar_wait(&chunk_done[set], (uint32_t)((chunk >> 1) & 1));
+                mbar_wait_relaxed(&chunk_done[set], (uint32_t)((chunk >> 1) & 1), 500);
                 tc_fence_after();
             }
             __syncwarp();
@@ -319,9 +317,10 @@ int param_grad_bf16_grid(int64_t n_paths, int64_t n_stage_total) {
 int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, const float* z_stages, const float* a_stages,
                         const int32_t* stage_index, const float* stage_frac, const float* stage_weight, int n_stage_total,
                         float* scratch, int64_t n_paths, int grid, cudaStream_t stream) {
-    constexpr int smem = pg2::kSmem + 1024;                // slack for the 1024-byte alignment of the tiles
-    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TCDE_CHECK_CUDA(cudaFuncSetAttribute(pg2::param_grad_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // 8 producer warps, 3 operand buffers + 4 staging slots, proxy fence in the producers: the A/B of the alternatives (16 warps,
+    // fence in the issuer, 2 + 7 / 3 + 3 rings) is in profiles/r02_pg_modes.txt -- all within 10 %, this one fastest
+    constexpr int kQ = 2, kBufs = 3, kSlots = 4;
+    constexpr int smem = pg2::smem_bytes(kBufs, kSlots) + 1024;   // + slack for the 1024-byte alignment of the tiles
     alignas(64) CUtensorMap rows_map;
     const int row_floats = (control_kind == TCDE_CONTROL_CUBIC) ? 4 * pg2::C : pg2::C;
     const int rc = tc::make_rows_tensor_map(&rows_map, control, n_paths, n_rows, row_floats, pg2::kPairs);
@@ -330,14 +329,10 @@ int param_grad_bf16_f32(const float* control, int control_kind, int64_t n_rows, 
     const int rca = tc::make_stage_tensor_map(&a_map, const_cast<float*>(a_stages), n_paths, n_stage_total, pg2::kPairs);
     const int rcz = tc::make_stage_tensor_map(&z_map, const_cast<float*>(z_stages), n_paths, n_stage_total, pg2::kPairs);
     TCDE_CHECK_SUPPORTED(rca == 0 && rcz == 0, "parameter gradients: cuTensorMapEncodeTiled failed (%d, %d) for the stage trajectories", rca, rcz);
-    // TCDE_PG_MODE (experiment switch, read once): bit 0 = 16 producer warps instead of 8, bit 1 = proxy fence in the issuer
-    static const int mode = [] { const char* v = getenv("TCDE_PG_MODE"); return v ? atoi(v) : 0; }();
-    if (mode & 1)
-        pg2::param_grad_bf16_kernel<4><<<grid, 640, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index, stage_frac,
-                                                                   stage_weight, n_stage_total, scratch, n_paths, rows_map, a_map, z_map, (mode >> 1) & 1);
-    else
-        pg2::param_grad_bf16_kernel<2><<<grid, 384, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index, stage_frac,
-                                                                   stage_weight, n_stage_total, scratch, n_paths, rows_map, a_map, z_map, (mode >> 1) & 1);
+    auto kern = pg2::param_grad_bf16_kernel<kQ, kBufs, kSlots>;
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 128 * kQ + 128, smem, stream>>>(control, control_kind, n_rows, z_stages, a_stages, stage_index, stage_frac, stage_weight,
+                                                 n_stage_total, scratch, n_paths, rows_map, a_map, z_map, 0);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }

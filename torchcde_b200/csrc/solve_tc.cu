@@ -69,9 +69,11 @@ template <int MODE> struct Smem {
     static constexpr int red = a_aug + kTiles * kTile * 32;                          // 64 floats of reduction scratch
     static constexpr int bars = red + 256;                                           // a_ready[2], d_ready[2], raw_full[2][2], tmem slot
     static constexpr int total = bars + 128;
-    // MODE 1 with a stage dump: one [128 rows x 128 B] staging tile per tile (TMA store source, 128-byte swizzle)
+    // MODE 1 with a stage dump: two [128 rows x 128 B] staging tiles per tile (TMA store source, 128-byte swizzle), used
+    // alternately: the store of stage s may still be reading its tile while the rows stage the input of stage s + 1
     static constexpr int dump = (total + 1023) & ~1023;
-    static constexpr int total_dump = dump + kTiles * kTile * 128;
+    static constexpr int dump_buf = kTile * 128;
+    static constexpr int total_dump = dump + kTiles * 2 * dump_buf;
 };
 
 __device__ __forceinline__ void reg_dealloc_24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::: "memory"); }
@@ -252,10 +254,10 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     if (kStaged) {
                         // this stage's input rows (staged by the row threads before their arrival) -> the trajectory in HBM.
                         // The commit that releases the row threads into the next stage is issued once the TMA unit has READ
-                        // the staging tile -- long before the 7 MMAs above have finished, so nobody waits for it
-                        tma_store_3d(&dump_map, smem + S::dump + t * kTile * 128, 0, (int)tile_path0, st);
+                        // the staging tile they will write next (the one of the PREVIOUS stage: a full period old)
+                        tma_store_3d(&dump_map, smem + S::dump + (2 * t + (st & 1)) * S::dump_buf, 0, (int)tile_path0, st);
                         bulk_commit();
-                        bulk_wait_read<0>();
+                        bulk_wait_read<1>();                  // the store of stage st - 1 has read the OTHER tile: the rows may refill it
                         mma_commit(&d_ready[t]);
                     }
                 }
@@ -281,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
             float inv_scale = 1.f;                        // MODE 1: 1 / (row scale * weight scale) of the stage in flight
 
             auto write_a = [&](const float* z, int stage_no) {   // next stage input -> split operand rows
-                if (kStaged) {                            // ... and, for the adjoint, to the trajectory in HBM (via the staging tile)
-                    unsigned char* row = smem + S::dump + t * kTile * 128 + r * 128;
+                if (kStaged) {                            // ... and, for the adjoint, to the trajectory in HBM (via a staging tile)
+                    unsigned char* row = smem + S::dump + (2 * t + (stage_no & 1)) * S::dump_buf + r * 128;
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4)
                         *reinterpret_cast<float4*>(row + ((c4 ^ (r & 7)) << 4)) = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
