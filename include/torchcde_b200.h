@@ -255,9 +255,7 @@ TCDE_API int tcde_set_trace_buffer(void* device_buffer);
 
 /* Natural-cubic / gap-fill kernel choice: 0 = the parallel kernels (windowed sweeps, warp per path)
  * when the path fits shared memory (default), 1 = one thread per series, 2 = parallel kernels
- * but the CTA-per-path natural-cubic kernel instead of the warp-per-path one, 3 = default kernels, but the gap fill
- * threads its hole list by walking every position instead of using the hole bytes recorded by the loads.  For tests /
- * benchmarks. */
+ * but the CTA-per-path natural-cubic kernel instead of the warp-per-path one.  For tests / benchmarks. */
 TCDE_API int tcde_set_natural_variant(int variant);
 
 /* Which kernel tcde_cdeint_fixed_linear launches for float32: 0 = automatic (the tcgen05 kernel

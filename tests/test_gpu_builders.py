@@ -145,14 +145,12 @@ def test_natural_cubic_kernel_variants(shape, knots):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("shape", [(70, 256, 8), (9, 100, 4), (5, 33, 12), (3, 20, 32), (4, 3, 8), (6, 2, 1),
-                                   (131, 17, 7), (40, 1000, 4), (3, 64, 1), (2, 2000, 16), (11, 200, 8), (7, 300, 4),
-                                   (5, 193, 8)])
+                                   (131, 17, 7), (40, 1000, 4), (3, 64, 1), (2, 2000, 16)])
 @pytest.mark.parametrize("rate", [0.3, 0.9])
 def test_linear_fill_kernel_variants(dtype, shape, rate):
-    """Channels <= 32 take the scan kernel (variant 0; fp32 with 4 or 8 channels and chunks of 64 positions builds its hole
-    list from the hole bytes the loads record, variant 3 walks every position instead); it must give the bits of the ballot
-    kernel (variant 2), of the one-thread-per-series kernel (variant 1) and of the oracle -- including all-NaN series,
-    leading / trailing gaps, gaps longer than a chunk, partial last chunks and -0.0 observations next to an imputed end point."""
+    """Channels <= 32 take the scan kernel (variant 0); it must give the bits of the ballot kernel (variant 2), of
+    the one-thread-per-series kernel (variant 1) and of the oracle -- including all-NaN series, leading / trailing
+    gaps, gaps longer than a chunk and -0.0 observations next to an imputed end point."""
     from torchcde_b200 import _lib
     gen = torch.Generator().manual_seed(sum(shape) + int(rate * 10))
     x = torch.randn(shape, generator=gen, dtype=torch.float64).to(dtype)
@@ -166,7 +164,7 @@ def test_linear_fill_kernel_variants(dtype, shape, rate):
         want = O.linear_knots(x, t)
         td = None if t is None else t.to(DEV)
         try:
-            for variant in (0, 3, 2, 1):
+            for variant in (0, 2, 1):
                 _lib.call("tcde_set_natural_variant", variant)
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")

@@ -244,13 +244,9 @@ constexpr int kFillDist = 11;                // payload = distance to next obser
 // ``padw``): shared by the stand-alone fill kernel and by the fused series -> Hermite kernel below.  Returns whether
 // this lane's chunk held a hole.  Must be called by the whole warp (shuffles); the caller separates it from the loads
 // and from the readers of the tile with __syncwarp().
-// ``hole_bytes`` (optional; chunks of exactly 64 positions, channels <= 8): byte i = bit c set when channel c of position i is
-// a hole, recorded by the loads.  With it the backward walk over all 64 positions of the chunk (ncu: 1,600 of the kernel's
-// 3,900 instructions per path, 23 per position with its divergent hole / observation branches) shrinks to: 4 shared loads,
-// a multiply per 4 positions to gather the lane's bits into two 32-bit masks, and one short trip per HOLE to write its payload.
 template <typename T, bool UNIT>
 __device__ __forceinline__ bool fill_tile_in_place(T* tile, const T* ts, int L, int C, int lgG,
-                                                   int padw, int lane, const unsigned char* hole_bytes = nullptr) {
+                                                   int padw, int lane) {
     using E = exact<T>;
     const int G = 1 << lgG;
     const int nch = (L + G - 1) >> lgG;                     // chunks in use (<= 32 / C)
@@ -263,55 +259,7 @@ __device__ __forceinline__ bool fill_tile_in_place(T* tile, const T* ts, int L, 
     // backward: thread the holes (payload: distance to the next observation / next hole of the chunk, 0 = none)
     int first_idx = kFillNone, last_idx = -1, head = -1;
     T last_val = T(0);
-    if (hole_bytes != nullptr) {
-        if (active) {
-            const int n = g1 - g0;
-            T* base = tile + word(g0) + c;
-            const uint4* hb = reinterpret_cast<const uint4*>(hole_bytes + g0);
-            uint32_t m[2] = {0u, 0u};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint4 v = hb[q];
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // bit c of each of the 4 bytes -> bits 24..27 of the product (no carries: the partial products fall on distinct bits)
-                    const uint32_t nib = ((((w4[k] >> c) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-                    m[q >> 1] |= nib << (4 * (4 * (q & 1) + k));
-                }
-            }
-            const uint32_t v_lo = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-            const uint32_t v_hi = n >= 64 ? 0xffffffffu : (n > 32 ? ((1u << (n - 32)) - 1u) : 0u);
-            m[0] &= v_lo;
-            m[1] &= v_hi;
-            const uint32_t o_lo = ~m[0] & v_lo, o_hi = ~m[1] & v_hi;
-            if (o_lo | o_hi) {
-                const int first_rel = o_lo ? __ffs((int)o_lo) - 1 : 31 + __ffs((int)o_hi);
-                const int last_rel = o_hi ? 63 - __clz((int)o_hi) : 31 - __clz((int)o_lo);
-                first_idx = g0 + first_rel;
-                last_idx = g0 + last_rel;
-                last_val = base[last_rel * C];
-            }
-            // thread the holes, highest position first (payload as below)
-            int next_hole = -1, d_obs_prev = 0;
-#pragma unroll
-            for (int half = 1; half >= 0; --half) {
-                uint32_t w = m[half];
-                while (w) {
-                    const int kb = 31 - __clz((int)w);
-                    w &= ~(1u << kb);
-                    const int k = kb + 32 * half;
-                    // next observation above k: right behind it, or wherever the hole above k found it
-                    const int d_obs = (next_hole == k + 1) ? (d_obs_prev ? d_obs_prev + 1 : 0) : (k + 1 < n ? 1 : 0);
-                    const int d_hole = next_hole >= 0 ? next_hole - k : 0;
-                    base[k * C] = nan_code<T>::make(d_obs | (d_hole << kFillDist));
-                    next_hole = k;
-                    d_obs_prev = d_obs;
-                }
-            }
-            head = next_hole >= 0 ? g0 + next_hole : -1;
-        }
-    } else if (active) {
+    if (active) {
         T* ptr = tile + word(g1 - 1) + c;
         for (int i = g1 - 1; i >= g0; --i, ptr -= C) {
             const T w = *ptr;
@@ -386,15 +334,11 @@ __device__ __forceinline__ bool fill_tile_in_place(T* tile, const T* ts, int L, 
 template <typename T, bool UNIT, int OUT>
 __global__ void __launch_bounds__(kThreads)
 linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __restrict__ out, int64_t n_paths, int L,
-                        int C, int lgG, int padw, int tile_words, int hole_stride, int32_t* __restrict__ flags) {
+                        int C, int lgG, int padw, int tile_words, int32_t* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using E = exact<T>;
     T* ts = reinterpret_cast<T*>(smem_raw);                 // knot times (absent for unit knots)
     T* tiles = ts + (UNIT ? 0 : ((L + 3) & ~3));
-    // hole_stride > 0 (fp32, channels 4 or 8, chunks of 64 positions, aligned pointers): one byte per position per warp
-    unsigned char* hole_bytes = hole_stride > 0
-        ? reinterpret_cast<unsigned char*>(tiles + (size_t)(kThreads / 32) * tile_words) + (size_t)(threadIdx.x >> 5) * hole_stride
-        : nullptr;
     if (!UNIT) {
         for (int i = threadIdx.x; i < L; i += blockDim.x) ts[i] = t[i];
         __syncthreads();
@@ -413,27 +357,7 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
         const T* xg = x + p * (int64_t)L * C;
         __syncwarp();                                       // the previous path has been copied out
         bool hole = false;
-        if (hole_bytes != nullptr) {
-            // the same loads, and every position's channel-hole byte on the side (Q = 1 or 2 lanes per position, uniform trip count)
-            const float4* xg4 = reinterpret_cast<const float4*>(xg);
-            const int n_items = L * Q;
-#pragma unroll 4
-            for (int e0 = 0; e0 < n_items; e0 += 32) {
-                const int e = e0 + lane;
-                const bool in = e < n_items;
-                const int i = (Q == 2) ? (e >> 1) : e, q = (Q == 2) ? (e & 1) : 0;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (in) v = __ldg(xg4 + e);
-                uint32_t bits = (is_nan(v.x) ? 1u : 0u) | (is_nan(v.y) ? 2u : 0u) | (is_nan(v.z) ? 4u : 0u) | (is_nan(v.w) ? 8u : 0u);
-                bits <<= 4 * q;
-                if (Q == 2) bits |= __shfl_xor_sync(full, bits, 1);
-                hole |= bits != 0u;
-                if (in) {
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(tile) + word(i) + 4 * q) = v;
-                    if (q == 0) hole_bytes[i] = (unsigned char)bits;
-                }
-            }
-        } else if (vec4) {
+        if (vec4) {
             const float4* xg4 = reinterpret_cast<const float4*>(xg);
             const int dq_i = 32 / Q, dq_q = 32 - dq_i * Q;
             int i = lane / Q, q = lane - (lane / Q) * Q;
@@ -462,7 +386,7 @@ linear_fill_scan_kernel(const T* __restrict__ x, const T* __restrict__ t, T* __r
         __syncwarp();
         if (__any_sync(full, hole)) {
             saw_nan = true;
-            fill_tile_in_place<T, UNIT>(tile, ts, L, C, lgG, padw, lane, hole_bytes);
+            fill_tile_in_place<T, UNIT>(tile, ts, L, C, lgG, padw, lane);
             __syncwarp();
         }
         if (OUT == 0) {
@@ -650,12 +574,7 @@ static int launch_fill_scan(const void* x, const void* t, void* out, int64_t n_p
     const int bank_words = (int)(128 / elem);
     const int padw = (int)((((int64_t)C - (int64_t)G * C) % bank_words + bank_words) % bank_words);
     const int tile_words = (L * C + nct * padw + 3) & ~3;
-    // hole bytes recorded by the loads (see fill_tile_in_place): fp32, 4 or 8 channels, chunks of 64 positions, 16-byte aligned
-    const bool masks = g_fill_variant != 3 && dtype == TCDE_F32 && (C == 4 || C == 8) && lgG == 6 &&
-                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    const int hole_stride = masks ? ((L + 63) & ~63) : 0;
-    const size_t smem = (t ? (size_t)((L + 3) & ~3) * elem : 0) + (size_t)(kThreads / 32) * tile_words * elem +
-                        (size_t)(kThreads / 32) * hole_stride;
+    const size_t smem = (t ? (size_t)((L + 3) & ~3) * elem : 0) + (size_t)(kThreads / 32) * tile_words * elem;
     if (!(smem <= 100 * 1024 && lgG < kFillDist)) return TCDE_ERR_UNSUPPORTED;   // hole-list distances are 11-bit
     const void* kern;
     if (what == 0)
@@ -670,7 +589,7 @@ static int launch_fill_scan(const void* x, const void* t, void* out, int64_t n_p
     const int grid = persistent_grid(kern, kThreads, smem, (n_paths + kThreads / 32 - 1) / (kThreads / 32));
     const int Li = L, Ci = C;
     void* args[] = {(void*)&x, (void*)&t, (void*)&out, (void*)&n_paths, (void*)&Li, (void*)&Ci, (void*)&lgG,
-                    (void*)&padw, (void*)&tile_words, (void*)&hole_stride, (void*)&flags};
+                    (void*)&padw, (void*)&tile_words, (void*)&flags};
     TCDE_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, smem, s));
     return TCDE_OK;
 }
@@ -700,7 +619,7 @@ extern "C" int tcde_linear_fill(const void* x, const void* t, void* out, int64_t
     if (n_series == 0) return TCDE_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int L = (int)length, C = (int)channels;
-    if (g_fill_variant == 0 || g_fill_variant == 3) {     // 3: the scan kernel without the hole bytes (A/B, tests)
+    if (g_fill_variant == 0) {
         rc = launch_fill_scan(x, t, out, n_paths, L, C, dtype, flags, s, 0);
         if (rc != TCDE_ERR_UNSUPPORTED) return rc;
     }
@@ -783,10 +702,9 @@ extern "C" int tcde_nan_flag(const void* x, int64_t n, int dtype, int32_t* flags
 }
 
 extern "C" int tcde_set_natural_variant(int variant) {
-    TCDE_CHECK_ARG(variant >= 0 && variant <= 3,
-                   "variant=%d (0 parallel kernels, 1 one thread per series, 2 CTA-per-path natural kernel, 3 gap fill without hole bytes)",
-                   variant);
-    g_natural_variant = variant == 3 ? 0 : variant;
+    TCDE_CHECK_ARG(variant >= 0 && variant <= 2,
+                   "variant=%d (0 parallel kernels, 1 one thread per series, 2 CTA-per-path natural kernel)", variant);
+    g_natural_variant = variant;
     g_fill_variant = variant;
     return TCDE_OK;
 }

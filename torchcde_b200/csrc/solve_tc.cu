@@ -247,18 +247,21 @@ __global__ void __launch_bounds__(kThreads, 1) cdeint_tc_kernel(const UmmaArgs a
                     if (tr) a.trace[st * 8 + 0] = clock64();
                     issue_tile<MODE>(tmem_base + (uint32_t)(t * kN), smem, smem + S::a + t * S::a_tile_bytes,
                                      smem + S::a_aug + t * kTile * 32, kStaged ? nullptr : &d_ready[t]);
+                    if (kStaged) {
+                        // the commit releases the row threads into the next stage, where they refill the staging tile of the
+                        // PREVIOUS stage: its store (issued a full period ago) must have read it
+                        bulk_wait_read<0>();
+                        mma_commit(&d_ready[t]);
+                    }
                     if (tr) a.trace[st * 8 + 1] = clock64();
                     ++kcount;
                     // the rows of the NEXT stage: their buffer was last read two stages ago, before the arrivals just waited for
                     if (st + 1 < st_hi) fetch_rows(kcount, idx_fetch);
                     if (kStaged) {
-                        // this stage's input rows (staged by the row threads before their arrival) -> the trajectory in HBM.
-                        // The commit that releases the row threads into the next stage is issued once the TMA unit has READ
-                        // the staging tile they will write next (the one of the PREVIOUS stage: a full period old)
+                        // this stage's input rows (staged by the row threads before their arrival) -> the trajectory in HBM,
+                        // off the chain: nobody waits for this store before the next stage's commit
                         tma_store_3d(&dump_map, smem + S::dump + (2 * t + (st & 1)) * S::dump_buf, 0, (int)tile_path0, st);
                         bulk_commit();
-                        bulk_wait_read<1>();                  // the store of stage st - 1 has read the OTHER tile: the rows may refill it
-                        mma_commit(&d_ready[t]);
                     }
                 }
             }
