@@ -10,8 +10,9 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key m
 
 Timing rules: inputs resident in HBM for ``value`` (CUDA events, max over ranks, barrier +
 synchronize both sides); the coefficient tensor is 2.1 GB per GPU, far larger than the 126 MB
-L2, so no flush is needed between iterations.  ``e2e`` runs the same solve from pinned HOST
-buffers through ``torchcde_b200.hostio.cdeint_from_host`` with the copies inside the timed region.
+L2, so no flush is needed between iterations.  ``e2e`` runs the user pipeline from pinned HOST
+series through ``torchcde_b200.hostio.cdeint_from_host_series`` (H2D of x and z0, fused gap fill +
+Hermite coefficients on the device, fused solve, D2H) with the copies inside the timed region.
 """
 import argparse
 import json
@@ -564,7 +565,7 @@ def run_gpu_arm(args):
         "gpu_launches": args.steps,
         "roofline": ({
             "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2228860000, "peak_source": peaks["source"],
+            "frac": achieved_tf / peaks["bf16_tflops"], "traffic": 2225915168, "peak_source": peaks["source"],
             "kernel": kernel_name,
             "algorithmic_flops_per_launch": BATCH * FLOPS_PER_SEQ,
             "note": "achieved = ALGORITHMIC flops (17.6 MFLOP/seq) / time against the measured dense bf16 peak, as the "

@@ -212,6 +212,13 @@ TCDE_API int tcde_linear_field_param_grads(const void* control, int control_kind
 TCDE_API int tcde_linear_combination(void* out, const void* base, const void* const* terms, const double* coefs,
                             int n_terms, int64_t n, int dtype, void* stream);
 
+/* The contraction that closes _VectorField.forward for an arbitrary func (solver.py:129-135):
+ * out[p][h] = scale * sum_c field[p][h][c] * dx[p * dx_stride + c]   (field [n_paths][hidden][channels] contiguous, out
+ * [n_paths][hidden]; dx may be a strided view, e.g. one stage of the per-step dX/dt block; scale = -1 for reversed time).
+ * torch.matmul runs this as a batched cuBLAS kernel at ~100 GB/s; streamed it is HBM bound. */
+TCDE_API int tcde_field_contract(const void* field, const void* dx, void* out, int64_t n_paths, int64_t hidden, int64_t channels,
+                        int64_t dx_stride, double scale, int dtype, void* stream);
+
 /* The error ratio of one attempted step (rk_common._compute_error_ratio, restated): with
  * err = sum_j coefs[j] * terms[j] and tol = atol + rtol * max(|y0|, |y1|), partials[c] receives the sum over
  * CTA c's elements of (err / tol)^2; the RMS norm is sqrt(sum(partials) / n).  partials: device double

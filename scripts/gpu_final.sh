@@ -4,6 +4,8 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_tests_final.txt 2>&1
 tail -4 gpurun_out/r02_tests_final.txt
+timeout 600 python scripts/soak_fence.py 40 > gpurun_out/r02_soak_fence.txt 2>&1
+tail -7 gpurun_out/r02_soak_fence.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_smoke_final.txt 2>&1
 tail -2 gpurun_out/r02_smoke_final.txt
 timeout 900 python bench.py --impl reference > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err

@@ -153,6 +153,30 @@ def test_generic_field_kernel_loop_and_cuda_graph(method, step):
         assert torch.allclose(fast, slow, rtol=1e-5, atol=1e-5)
         assert torch.allclose(graph, fast, rtol=1e-6, atol=1e-6)
         assert torch.allclose(again, half, rtol=1e-6, atol=1e-6)          # the replay really read the new z0
+        # reversed time: the sign is folded into the contraction kernel (tcde_field_contract)
+        t_rev = torch.tensor([19.0, 7.3, 0.0])
+        with torch.no_grad():
+            fast_rev = cde.cdeint(X, func, z0, t_rev, adjoint=False, method=method, options={"step_size": step})
+            slow_rev = solver._generic_solve(X, func, z0, t_rev, method, step, False, True)
+        assert torch.allclose(fast_rev, slow_rev, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_field_contract_kernel_against_matmul(dtype):
+    """solver.py:129-135: (f @ dX.unsqueeze(-1)).squeeze(-1) as tcde_field_contract, with dX a strided view."""
+    from torchcde_b200 import _lib
+    torch.manual_seed(3)
+    P, H, C, S = 77, 13, 5, 4
+    f = torch.randn(P, H, C, device=DEV, dtype=dtype)
+    dxs = torch.randn(P, S, C, device=DEV, dtype=dtype)
+    for s in range(S):
+        for scale in (1.0, -1.0):
+            out = torch.empty(P, H, device=DEV, dtype=dtype)
+            _lib.call("tcde_field_contract", _lib.ptr(f), _lib.ptr(dxs[:, s]), _lib.ptr(out), P, H, C, S * C, scale,
+                      _lib.dtype_code(dtype), _lib.stream_of(f))
+            want = scale * (f.double() @ dxs[:, s].double().unsqueeze(-1)).squeeze(-1)
+            tol = 1e-5 if dtype == torch.float32 else 1e-13
+            assert torch.allclose(out.double(), want, rtol=tol, atol=tol)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])

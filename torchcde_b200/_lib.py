@@ -26,6 +26,7 @@ SIGNATURES = {
     "tcde_last_error": ([], ctypes.c_char_p),
     "tcde_device_info": ([_p, _p, _p], _int),
     "tcde_hermite_bdiff_coeffs": ([_p, _p, _p, _i64, _i64, _i64, _int, _p, _p], _int),
+    "tcde_field_contract": ([_p, _p, _p, _i64, _i64, _i64, _i64, ctypes.c_double, _int, _p], _int),
     "tcde_hermite_bdiff_coeffs_series": ([_p, _p, _p, _i64, _i64, _i64, _int, _p, _p], _int),
     "tcde_linear_fill": ([_p, _p, _p, _i64, _i64, _i64, _int, _p, _p], _int),
     "tcde_nan_flag": ([_p, _i64, _int, _p, _p], _int),

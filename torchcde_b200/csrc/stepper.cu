@@ -62,6 +62,24 @@ error_kernel(const T* __restrict__ y0, const T* __restrict__ y1, const Terms<T> 
     }
 }
 
+// _VectorField.forward's last line (solver.py:129-135) for an arbitrary func: out[p][h] = scale * sum_c f[p][h][c] * dx[p][c].
+// torch.matmul hands this (batch of [H x C] . [C]) to a batched cuBLAS kernel: 62 us for 65,536 x 8 x 3 (100 GB/s); streamed
+// it is a few microseconds.  dx may be a strided view (the stages of a step side by side): dx_stride elements per path.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+contract_kernel(const T* __restrict__ f, const T* __restrict__ dx, T* __restrict__ out, int64_t n_rows, int hidden, int channels,
+                int64_t dx_stride, T scale) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n_rows; i += stride) {     // i = path * hidden + h
+        const int64_t p = i / hidden;
+        const T* fr = f + i * channels;
+        const T* dr = dx + p * dx_stride;
+        T acc = T(0);
+        for (int c = 0; c < channels; ++c) acc = fma(fr[c], dr[c], acc);
+        out[i] = scale * acc;
+    }
+}
+
 static int stepper_grid(int64_t n) {
     int64_t g = (n + kThreads * 4 - 1) / (kThreads * 4);
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -102,6 +120,26 @@ extern "C" int tcde_linear_combination(void* out, const void* base, const void* 
     else
         stepper::combine_kernel<double><<<grid, stepper::kThreads, 0, s>>>((double*)out, (const double*)base,
                                                                           stepper::make_terms<double>(terms, coefs, n_terms), n);
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
+extern "C" int tcde_field_contract(const void* field, const void* dx, void* out, int64_t n_paths, int64_t hidden, int64_t channels,
+                                   int64_t dx_stride, double scale, int dtype, void* stream) {
+    TCDE_CHECK_ARG(field && dx && out, "null pointer");
+    TCDE_CHECK_ARG(n_paths >= 0 && hidden >= 1 && channels >= 1 && dx_stride >= channels, "bad sizes");
+    TCDE_CHECK_ARG(dtype == TCDE_F32 || dtype == TCDE_F64, "dtype=%d", dtype);
+    TCDE_CHECK_SUPPORTED(hidden < (1ll << 31) && channels < (1ll << 31), "hidden / channels too large");
+    const int64_t n = n_paths * hidden;
+    if (n == 0) return TCDE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = stepper::stepper_grid(n * 4);
+    if (dtype == TCDE_F32)
+        stepper::contract_kernel<float><<<grid, stepper::kThreads, 0, s>>>((const float*)field, (const float*)dx, (float*)out, n, (int)hidden,
+                                                                          (int)channels, dx_stride, (float)scale);
+    else
+        stepper::contract_kernel<double><<<grid, stepper::kThreads, 0, s>>>((const double*)field, (const double*)dx, (double*)out, n,
+                                                                           (int)hidden, (int)channels, dx_stride, scale);
     TCDE_CHECK_CUDA(cudaGetLastError());
     return TCDE_OK;
 }

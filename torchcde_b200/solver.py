@@ -346,9 +346,23 @@ def _generic_solve_kernels(X, func, z0, t, method, step_size, is_prod, use_graph
             def field(s, z):
                 ts = times_dev[i, s]
                 dx = dxs[..., s, :]
-                out = func.prod(ts, z, dx) if is_prod else (func(ts, z) @ dx.unsqueeze(-1)).squeeze(-1)
-                out = out if sign > 0 else -1.0 * out
-                return out if out.is_contiguous() else out.contiguous()
+                if is_prod:
+                    out = func.prod(ts, z, dx)
+                    out = out if sign > 0 else -1.0 * out
+                    return out if out.is_contiguous() else out.contiguous()
+                # solver.py:129-135: f(t, z) @ dX/dt as one streaming launch (the sign of a reversed solve folded in)
+                f = func(ts, z)
+                if (f.shape != z.shape + (channels,) or f.dtype != dtype or dxs.dtype != dtype or not f.is_cuda
+                        or dxs.shape[:-2] != z.shape[:-1]):
+                    out = (f @ dx.unsqueeze(-1)).squeeze(-1)          # an unusual func output: let torch broadcast / promote
+                    out = out if sign > 0 else -1.0 * out
+                    return out if out.is_contiguous() else out.contiguous()
+                f = f if f.is_contiguous() else f.contiguous()
+                out = torch.empty_like(z)
+                _lib.call("tcde_field_contract", _lib.ptr(f), _lib.ptr(dx), _lib.ptr(out), z.numel() // z.size(-1), z.size(-1),
+                          channels, n_stages * channels, float(sign),
+                          _lib.dtype_code(dtype), _lib.stream_of(z))
+                return out
 
             dt = float(sched.step_dt[i])
             if method == "rk4":
