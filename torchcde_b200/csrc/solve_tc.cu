@@ -18,7 +18,15 @@
 //   * the spline rows come by TMA: one cp.async.bulk.tensor per tile and stage (box = 128 paths x one interval's
 //     a|b|2c|3d, 128B swizzle, double buffered, issued by the tile's MMA issuer a stage ahead).  The per-thread cp.async
 //     of round 1 touched 32 cache lines per warp instruction: 1,536 L1 cycles per stage on the SM's one LSU pipe;
-//   * 32-column TMEM loads (the next in flight while the current is contracted), a tree for the row maximum;
+//   * 16-column TMEM loads, the next in flight while the current is contracted (the contraction runs at 82 % of the TMEM
+//     read rate of 64 B/cycle per sub-partition: 626 cycles for a tile's 128 KB), a tree for the row maximum;
+//   * ONE proxy fence per tile and stage, executed by the issuer after it has acquired a_ready, instead of one per row
+//     thread on the critical chain (the arrivals' release + the issuer's acquire order the rows' generic-proxy stores
+//     before that fence; scripts/soak_fence.py checks bit-identity with the row-fenced variant, debug bit 1);
+//   * the two tiles run in anti-phase (a nanosleep for tile 1 once per unit): started together they stay in lockstep and
+//     queue behind each other's 7 MMAs every stage;
+//   * DUMP (the adjoint's stage trajectory): staged in a swizzled tile, one TMA tensor store per tile and stage issued
+//     after the commit -- 32 threads storing 128 B each straight to HBM cost 32 lines per instruction (5.9 vs 3.56 ms);
 //   * persistent CTAs (one per SM) over work units (pair of tiles, segment of the time axis): 256 pairs x 4 segments over
 //     148 SMs is 6.9 -> 7 rounds of a quarter solve = 1.75 solves per SM instead of 2.  A unit starts from the state its
 //     predecessor left in HBM (32 floats per path) once that unit's flag is up; units are dealt round-robin in
