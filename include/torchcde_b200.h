@@ -233,7 +233,7 @@ TCDE_API int tcde_error_ratio_sumsq(const void* y0, const void* y1, const void* 
  * requested times run on the device, so the host only reads the control block once per chunk of launches.
  *   state     float  [5][n_paths][32]: Y0, Y1, F0, F1, MID.  Before the first launch Y0 = y(t0), F0 = f(t0, y(t0)).
  *   partials  double [2][tcde_dopri5_linear_grid(n_paths)]
- *   ctl       double [2][16]: slot 1 is read by launch 0.  Fields: 0 t, 1 dt, 2 t_end, 3 rtol, 4 atol, 5 current state
+ *   ctl       double [2][24]: slot 1 is read by launch 0.  Fields: 0 t, 1 dt, 2 t_end, 3 rtol, 4 atol, 5 current state
  *             buffer, 6 done, 7 pending (an undecided attempt exists), 8 accepted, 9 rejected, 10 next output index (>= 1),
  *             11 number of partials, 12 need_mid, 13 last error ratio, 14 launches.  Launch seq reads slot (seq + 1) & 1
  *             and writes slot seq & 1.
@@ -245,6 +245,25 @@ TCDE_API int tcde_dopri5_linear_attempts(const void* control, int control_kind, 
                                 const void* weight, const void* bias, void* state, void* partials, void* ctl, void* out,
                                 const void* out_times, int64_t n_out, int64_t n_paths, int64_t channels, int64_t hidden,
                                 double sign, int64_t first_seq, int64_t n_launches, int dtype, void* stream);
+
+/* The backward pass of cdeint(adjoint=True) with dopri5 for the linear field, controller on the device (torchdiffeq's
+ * odeint_adjoint behind torchcde/solver.py:226-227 with the default method): a VIRTUAL batch of 2 n_ctrl paths -- the first half
+ * the state z with (weight, bias), the second half the adjoint state a with (weight2, bias2) = the regrouped, negated weight and a
+ * zero bias -- advances with one step-size controller (RMS error norm over both halves).  state [5][2 n_ctrl][32], out
+ * [2 n_ctrl][n_out][32], ctl / partials as for tcde_dopri5_linear_attempts (grid for 2 n_ctrl paths); ctl field 15 = slots full, 16 = slot base.
+ * Every attempt stores the inputs of its stages 1, 3, 4, 5, 6 into slot [accepted steps so far] of dump_z / dump_a
+ * [max_slots][5][n_ctrl][32]; for every accepted step the controller writes the five quadrature nodes q_index / q_frac /
+ * q_weight [max_slots * 5] (spline interval, fraction, dt * b_i), so that ONE call of tcde_linear_field_param_grads over
+ * 5 * accepted stages yields dL/dW, dL/db.  When the slots are full the solve pauses (done = 1, field 15 = 1): the caller
+ * contracts the filled slots, sets field 16 to the number of accepted steps, clears fields 6 and 15 of the slot just
+ * read, and enqueues more launches.
+ * n_ctrl must be a multiple of 256.  float32, hidden = 32, channels = 8. */
+TCDE_API int tcde_dopri5_linear_paired_attempts(const void* control, int control_kind, int64_t n_rows, const void* knots,
+                                       const void* weight, const void* bias, const void* weight2, const void* bias2, void* state,
+                                       void* partials, void* ctl, void* out, const void* out_times, int64_t n_out, int64_t n_ctrl,
+                                       int64_t channels, int64_t hidden, double sign, void* dump_z, void* dump_a,
+                                       int32_t* q_index, void* q_frac, void* q_weight, int64_t max_slots, int64_t first_seq,
+                                       int64_t n_launches, int dtype, void* stream);
 
 /* Logsignatures of windows of piecewise-linear paths -- replaces the per-window call of the optional third-party package
  * at torchcde/log_ode.py:56-58 (``signatory.Logsignature(depth)``, default "words" basis).  x [n_paths][length][channels]

@@ -406,3 +406,57 @@ def test_parameter_gradient_kernels_against_einsum(n_paths, n_stages, kind):
                 assert float((got - want).abs().max()) <= bar * max(1.0, float(want.abs().max())), variant
     finally:
         _lib.call("tcde_set_solve_variant", 0)
+
+
+@pytest.mark.parametrize("kind", ["cubic", "linear"])
+@pytest.mark.parametrize("slots", [None, 16])
+def test_device_controlled_dopri5_adjoint_matches_the_host_driven_adjoint(kind, slots, monkeypatch):
+    """cdeint(adjoint=True) with the default dopri5: the backward pass with the controller on the device
+    (tcde_dopri5_linear_paired_attempts: z and the adjoint state as one virtual batch, parameter gradients by quadrature over
+    the accepted steps' stage inputs) against this package's host-driven adjoint (one fused field + vjp launch per evaluation)
+    at a tolerance tight enough to compare them; two segments between three output times; with 16 trajectory slots the
+    device has to pause and hand the slots back several times."""
+    from torchcde_b200 import adaptive, solver
+    torch.manual_seed(11)
+    B, L, C, H = 512, 14, 8, 32
+    x = torch.randn(B, L, C, device=DEV).cumsum(1) / 3
+    X = (cde.CubicSpline(cde.hermite_cubic_coefficients_with_backward_differences(x)) if kind == "cubic"
+         else cde.LinearInterpolation(x))
+    func = cde.LinearVectorField(H, C).to(DEV)
+    with torch.no_grad():
+        func.linear.weight.mul_(0.5)
+    z0 = torch.randn(B, H, device=DEV)
+    t = torch.tensor([0.0, 5.5, L - 1.0], device=DEV)
+    kw = {"rtol": 1e-6, "atol": 1e-8}
+
+    def run():
+        zz = z0.clone().requires_grad_(True)
+        func.zero_grad()
+        out = cde.cdeint(X, func, zz, t, adjoint=True, **kw)
+        (out[:, -1].sum() + (out[:, 1] ** 2).sum()).backward()
+        return out.detach(), zz.grad.clone(), func.linear.weight.grad.clone(), func.linear.bias.grad.clone()
+
+    if slots is not None:
+        real = solver._kernel_vjp
+
+        def with_few_slots(*a, **k):
+            st = real(*a, **k)
+            if st is not None:
+                st.slots_hint = slots
+            return st
+
+        monkeypatch.setattr(solver, "_kernel_vjp", with_few_slots)
+    cde.cdeint.last_adjoint_stats = None
+    out_d, gz_d, gw_d, gb_d = run()
+    stats = cde.cdeint.last_adjoint_stats
+    assert stats is not None and stats["device_controlled"] and stats["n_accepted"] > 10
+    if slots is not None:
+        assert stats["flushes"] >= 1 and stats["slots"] == 16
+    monkeypatch.setattr(adaptive, "_device_adaptive_backward", lambda *a, **k: None)
+    cde.cdeint.last_adjoint_stats = None
+    out_h, gz_h, gw_h, gb_h = run()
+    assert cde.cdeint.last_adjoint_stats is None
+    assert torch.equal(out_d, out_h)
+    for got, want in ((gz_d, gz_h), (gw_d, gw_h), (gb_d, gb_h)):
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 2e-3 * scale, (float((got - want).abs().max()), scale)

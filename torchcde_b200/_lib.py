@@ -51,6 +51,8 @@ SIGNATURES = {
     "tcde_cdeint_fixed_linear": ([_p, _int, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _int, _i64, _p, _p, _p, _i64,
                                   _p, _p, _p, _dbl, _int, _p], _int),
     "tcde_dopri5_linear_grid": ([_i64], _int),
+    "tcde_dopri5_linear_paired_attempts": ([_p, _int, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _dbl,
+                                            _p, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p], _int),
     "tcde_dopri5_linear_attempts": ([_p, _int, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _dbl, _i64, _i64,
                                      _int, _p], _int),
     "tcde_logsignature_max_terms": ([], _i64),

@@ -262,7 +262,7 @@ def odeint_dopri5_device(control, kind, n_rows, knots, weight, bias, field, y0, 
         state[2].copy_(f0)
         grid = lib.tcde_dopri5_linear_grid(n_paths)
         partials = torch.zeros(2, grid, dtype=torch.float64, device=dev)
-        ctl_host = torch.zeros(2, 16, dtype=torch.float64)
+        ctl_host = torch.zeros(2, 24, dtype=torch.float64)
         ctl_host[1, 0], ctl_host[1, 1], ctl_host[1, 2] = t0, dt, times[-1]
         ctl_host[1, 3], ctl_host[1, 4] = rtol, atol
         ctl_host[1, 10] = 1                       # next output index
@@ -352,6 +352,11 @@ class _Adjoint(torch.autograd.Function):
             return (None, None, None, None, None, None, None, None, a_y, *a_p)
         if ctx.t_needs_grad:
             return _Adjoint._backward_with_times(ctx, ys, params, grad_ys)
+        if ctx.fused_vjp is not None and getattr(ctx.fused_vjp, "adaptive_spec", None) is not None:
+            with torch.no_grad():
+                done = _device_adaptive_backward(ctx.fused_vjp, times, ys, grad_ys)
+            if done is not None:
+                return (None, None, None, None, None, None, None, None, done[0], *done[1])
         shapes = [ys[0].shape, ys[0].shape] + [p.shape for p in params]
         sizes = [s.numel() for s in shapes]
 
@@ -443,6 +448,32 @@ class _Adjoint(torch.autograd.Function):
                 grad_t = -grad_t
             grad_t = grad_t.to(dtype=ctx.t_meta[0], device=ctx.t_meta[1])
         return (None, None, None, None, None, None, None, grad_t, a_y, *a_p)
+
+
+def _device_adaptive_backward(stage, times, ys, grad_ys):
+    """The dopri5 backward solve of ``_Adjoint`` with the controller on the device (``stage.adaptive_segment``), segment by
+    segment between the output times like torchdiffeq's ``odeint_adjoint``.  Returns ``(a_y, grads)`` or None when a segment
+    could not run there (the host-driven backward then starts from scratch)."""
+    rtol, atol = stage.adaptive_spec
+    grads = stage.new_grads()
+    gw = next((g for g, r in zip(grads, stage.roles) if r == "w"), None)
+    gb = next((g for g, r in zip(grads, stage.roles) if r == "b"), None)
+    from .solver import cdeint
+    hint = getattr(stage, "slots_hint", None) or 256
+    totals = {}
+    a_y = grad_ys[-1].clone()
+    for i in range(len(times) - 1, 0, -1):
+        a_lo = stage.adaptive_segment(times[i], times[i - 1], ys[i], a_y, rtol, atol, gw, gb, hint)
+        if a_lo is None:
+            return None
+        for key, val in stage.adaptive_stats.items():
+            totals[key] = max(totals.get(key, 0), val) if key == "slots" else totals.get(key, 0) + val
+        a_y = a_lo + grad_ys[i - 1]
+    try:
+        cdeint.last_adjoint_stats = dict(totals, device_controlled=True)
+    except Exception:
+        pass
+    return a_y, grads
 
 
 def _fused_fixed_backward(stage, times, ys, grad_ys, method, step_size):

@@ -20,6 +20,18 @@
 //     the 5th-order weights, the error weights and the dense output, so k6 takes its registers); stage times ->
 //     spline interval and fraction with the reference's bucketize semantics on the device; error partial sums of
 //     (err / (atol + rtol max(|y0|, |y1|)))^2 in double; candidate (y1, k7) into the other state buffer.
+//
+// PAIRED mode (the backward pass of cdeint(adjoint=True) with dopri5, weight2 != NULL): the batch is a VIRTUAL batch of
+// 2 n_ctrl paths -- paths [0, n_ctrl) carry the state z with (weight, bias), paths [n_ctrl, 2 n_ctrl) the adjoint state a
+// with the regrouped, negated weight (for this linear field da/ds = a^T df/dz does not involve z: two linear CDEs that share
+// the control and the step-size controller; the RMS error norm runs over both halves).  The parameter gradients
+// dL/dW, dL/db = integral of (a (x) dX) (x) (z | 1) are NOT carried as a third state: g' does not depend on g, so
+// integrating it with the same Runge-Kutta method is the quadrature  sum over accepted steps of dt * b_i * G(stage i) --
+// every attempt leaves the inputs of its stages 1, 3, 4, 5, 6 (the non-zero b_i) in slot [number of accepted steps so far]
+// of two trajectories (a rejected attempt is simply overwritten by the next one), the controller writes the accepted steps'
+// quadrature nodes (spline interval, fraction, dt * b_i), and ONE launch of the parameter-gradient GEMM
+// (param_grad_bf16.cu) contracts them afterwards.  (Not part of the error norm: in the host-driven adjoint the 8,448
+// parameter-gradient components are 0.2 % of the packed state's RMS.)
 #include "tc_common.cuh"
 
 namespace tcde {
@@ -30,10 +42,12 @@ using namespace tc;
 
 constexpr int kTiles = 2;
 constexpr int kThreads = kRows * kTiles;          // 256: thread = path; lane 0 of a tile's first warp issues its MMAs
-constexpr int kCtl = 16;                          // doubles per control slot
+constexpr int kCtl = 24;                          // doubles per control slot
 
 // control slot fields (doubles; the integer ones hold exact small integers)
-enum { C_T = 0, C_DT, C_TEND, C_RTOL, C_ATOL, C_CUR, C_DONE, C_PENDING, C_NACC, C_NREJ, C_NEXT_OUT, C_NPART, C_NEED_MID, C_RATIO, C_LAUNCHES };
+enum { C_T = 0, C_DT, C_TEND, C_RTOL, C_ATOL, C_CUR, C_DONE, C_PENDING, C_NACC, C_NREJ, C_NEXT_OUT, C_NPART, C_NEED_MID, C_RATIO, C_LAUNCHES,
+       C_OVERFLOW,     // paired mode: the trajectory slots are full -- the solve pauses (done = 1) until the caller has contracted them
+       C_BASE };       // paired mode: accepted steps already contracted; slot of an attempt = accepted steps - base
 
 __constant__ double c_alpha[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
 __constant__ double c_beta[6][6] = {
@@ -62,6 +76,16 @@ struct Args {
     int64_t n_paths, n_rows;
     int control_kind, n_out, seq;
     float sign;               // +1, or -1 for a decreasing t (the field is then -f(-s, y))
+    // paired mode (all null / zero otherwise)
+    const float* weight2;     // weights of the second half of the virtual batch
+    const float* bias2;
+    int64_t n_ctrl;           // paths of the control: n_paths, or n_paths / 2 in paired mode
+    float* dump_z;            // [max_slots][5][n_ctrl][32]: stage inputs of the first half
+    float* dump_a;            // ... of the second half
+    int32_t* q_index;         // [max_slots * 5] quadrature nodes of the accepted steps
+    float* q_frac;
+    float* q_weight;
+    int max_slots;
 };
 
 struct Smem {
@@ -91,7 +115,21 @@ struct Plan {
     float stage_frac[6];
     int stage_index[6];
     float rtol, atol;
+    int slot;                 // paired mode: trajectory slot of this attempt = accepted steps so far
 };
+
+// stage time -> (spline interval, fraction): the time in the state dtype, then the coefficient dtype (both float here), then
+// bucketize - 1 (the reference's _interpret_t on the device)
+__device__ __forceinline__ void locate_stage(const Args& a, double ti, int& idx, float& frac) {
+    const float tk = (float)((double)a.sign * ti);
+    int lo = 0, hi = (int)a.n_rows + 1;                    // lower_bound over knots[0 .. n_rows]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a.knots[mid] < tk) lo = mid + 1; else hi = mid;
+    }
+    idx = min(max(lo - 1, 0), (int)a.n_rows - 1);
+    frac = tk - a.knots[idx];
+}
 
 __device__ __forceinline__ double next_step(double dt, double ratio) {           // adaptive._next_step
     if (ratio == 0.0) return dt * 10.0;
@@ -137,8 +175,24 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             if (ratio <= 1.0) {
                 p.t_lo = t;
                 p.t_hi = t + dt;
+                // paired mode clips the last step to the end of the segment (below): land on it exactly
+                if (a.weight2 != nullptr && p.t_hi >= t_end - 1e-13 * fmax(1.0, fabs(t_end))) p.t_hi = t_end;
                 p.old_cur = cur;
                 cur ^= 1;
+                const int slot_acc = nacc - (int)in[C_BASE];
+                if (a.weight2 != nullptr && blockIdx.x == 0) {
+                    // the accepted step's quadrature nodes for the parameter gradients: stages 1, 3, 4, 5, 6
+                    const double cq[5] = {0.0, c_alpha[1], c_alpha[2], c_alpha[3], 1.0};
+                    const int bq[5] = {0, 2, 3, 4, 5};
+                    for (int k = 0; k < 5; ++k) {
+                        int idx;
+                        float fr;
+                        locate_stage(a, (cq[k] == 1.0) ? t + dt : t + cq[k] * dt, idx, fr);
+                        a.q_index[slot_acc * 5 + k] = idx;
+                        a.q_frac[slot_acc * 5 + k] = fr;
+                        a.q_weight[slot_acc * 5 + k] = (float)(c_beta[5][bq[k]] * dt);
+                    }
+                }
                 ++nacc;
                 p.emit_lo = next_out;
                 while (next_out < a.n_out && a.out_times[next_out] <= p.t_hi) ++next_out;
@@ -150,7 +204,16 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             }
             dt = next_step(dt, ratio);
         }
-        (void)t_end;
+        int overflow = (int)in[C_OVERFLOW];
+        const int base = (int)in[C_BASE];
+        if (a.weight2 != nullptr && !done && nacc - base >= a.max_slots) {   // no trajectory slot left for another attempt
+            overflow = 1;
+            done = 1;
+        }
+        p.slot = nacc - base;
+        // paired mode: the parameter gradients are a quadrature over WHOLE accepted steps, so the last step of a segment must end
+        // at the segment's end instead of running past it and interpolating back (what the plain solve, like torchdiffeq, does)
+        if (a.weight2 != nullptr && !done && t + dt > t_end) dt = t_end - t;
         p.t = t;
         p.dt = dt;
         p.cur = cur;
@@ -161,17 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
         if (!done) {
             for (int s = 0; s < 6; ++s) {
                 for (int j = 0; j < 6; ++j) p.cs[s][j] = (float)(c_beta[s][j] * dt);
-                // the stage time in the state dtype, then the coefficient dtype (both float here), then bucketize - 1
                 const double ti = (c_alpha[s] == 1.0) ? t + dt : t + c_alpha[s] * dt;
-                const float tk = (float)((double)a.sign * ti);
-                int lo = 0, hi = (int)a.n_rows + 1;            // lower_bound over knots[0 .. n_rows]
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (a.knots[mid] < tk) lo = mid + 1; else hi = mid;
-                }
-                const int idx = min(max(lo - 1, 0), (int)a.n_rows - 1);
-                p.stage_index[s] = idx;
-                p.stage_frac[s] = tk - a.knots[idx];
+                locate_stage(a, ti, p.stage_index[s], p.stage_frac[s]);
             }
             for (int j = 0; j < 7; ++j) {
                 p.ce[j] = (float)(c_err[j] * dt);
@@ -185,6 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             o[C_CUR] = cur; o[C_DONE] = done; o[C_PENDING] = done ? 0 : 1; o[C_NACC] = nacc; o[C_NREJ] = nrej;
             o[C_NEXT_OUT] = next_out; o[C_NPART] = gridDim.x; o[C_NEED_MID] = p.need_mid; o[C_RATIO] = ratio;
             o[C_LAUNCHES] = in[C_LAUNCHES] + 1.0;
+            o[C_OVERFLOW] = overflow;
+            o[C_BASE] = base;
         }
     }
     __syncthreads();
@@ -272,13 +328,32 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
     const bool need_mid = plan->need_mid != 0;
     double err_acc = 0.0;
 
+    const bool paired = a.weight2 != nullptr;         // then n_ctrl is a multiple of 256: no partial tiles, no pair across the halves
+    int cur_half = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const int64_t path = (pair * kTiles + t_) * kRows + r;
         const bool tile_live = (pair * kTiles + t_) * kRows < a.n_paths;
+        const int half = (paired && pair * kTiles * kRows >= a.n_ctrl) ? 1 : 0;
+        if (half != cur_half) {                       // CTA-uniform: switch the operand B to the adjoint state's weights
+            tc_fence_before();
+            __syncthreads();                          // every MMA that read the old weights has been waited for
+            prepare_b_fp16(smem + Smem::b, smem + Smem::b_aug, a.weight2, a.bias2, red, tid, kThreads, w_scale, inv_w_scale, beta);
+            fence_proxy_async_smem();
+            __syncthreads();
+            cur_half = half;
+        }
         if (!tile_live) continue;                     // whole tile beyond the batch: its four warps skip together
         const bool live = path < a.n_paths;
         const int64_t lpath = live ? path : a.n_paths - 1;
-        const float* crow = a.control + lpath * a.n_rows * row_stride + (cubic ? kCh : 0);
+        const int64_t cpath = lpath - (half ? a.n_ctrl : 0);      // the control's path (both halves share it)
+        const float* crow = a.control + cpath * a.n_rows * row_stride + (cubic ? kCh : 0);
+        float* dump = paired ? (half ? a.dump_a : a.dump_z) + ((size_t)plan->slot * 5 * a.n_ctrl + cpath) * kHid : nullptr;
+        auto dump_stage = [&](int k, const float* v) {           // input of quadrature stage k (0..4) of this attempt
+            if (!paired) return;
+            float4* dst = reinterpret_cast<float4*>(dump + (size_t)k * a.n_ctrl * kHid);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        };
 
         auto fetch_row = [&](int idx) {
             const float* src = crow + (int64_t)idx * row_stride;
@@ -343,6 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             }
         }
         fetch_row(plan->stage_index[0]);
+        dump_stage(0, y);
 
         // stage inputs y + sum_j c[s][j] k_j, fma in the order of adaptive._combine (zero weights skipped)
         // s = 0: k1
@@ -352,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
         // s = 1: k1, k2
 #pragma unroll
         for (int h = 0; h < kHid; ++h) kv[h] = fmaf(plan->cs[1][1], kA[h], fmaf(plan->cs[1][0], k1[h], y[h]));
+        dump_stage(1, kv);
         evaluate(kv, 1, kv, nothing);                                        // kv = k3
 #pragma unroll
         for (int h = 0; h < kHid; ++h) park[(size_t)(0 * kHid + h) * kRows] = kv[h];
@@ -359,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
 #pragma unroll
         for (int h = 0; h < kHid; ++h)
             kv[h] = fmaf(plan->cs[2][2], kv[h], fmaf(plan->cs[2][1], kA[h], fmaf(plan->cs[2][0], k1[h], y[h])));
+        dump_stage(2, kv);
         evaluate(kv, 2, kv, nothing);                                        // kv = k4
 #pragma unroll
         for (int h = 0; h < kHid; ++h) park[(size_t)(1 * kHid + h) * kRows] = kv[h];
@@ -369,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             v = fmaf(plan->cs[3][2], park[(size_t)(0 * kHid + h) * kRows], v);
             kv[h] = fmaf(plan->cs[3][3], kv[h], v);
         }
+        dump_stage(3, kv);
         evaluate(kv, 3, kv, nothing);                                        // kv = k5
 #pragma unroll
         for (int h = 0; h < kHid; ++h) park[(size_t)(2 * kHid + h) * kRows] = kv[h];
@@ -380,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_attempt_kernel(const Args 
             v = fmaf(plan->cs[4][3], park[(size_t)(1 * kHid + h) * kRows], v);
             kv[h] = fmaf(plan->cs[4][4], kv[h], v);
         }
+        dump_stage(4, kv);
         evaluate(kv, 4, kA, nothing);                                        // kA = k6 (k2 is not used again)
         // s = 5: the 5th-order solution y1 = y + dt (b1 k1 + b3 k3 + b4 k4 + b5 k5 + b6 k6); k7 = f(t + dt, y1)
         float y1[kHid];
@@ -464,6 +544,18 @@ extern "C" int tcde_dopri5_linear_grid(int64_t n_paths) {
     return (int)(pairs < sm_count() ? pairs : sm_count());
 }
 
+static int launch_attempts(dp5::Args a, int64_t first_seq, int64_t n_launches, cudaStream_t s) {
+    constexpr int smem = dp5::Smem::total + 1024;
+    TCDE_CHECK_CUDA(cudaFuncSetAttribute(dp5::dopri5_attempt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = tcde_dopri5_linear_grid(a.n_paths);
+    for (int64_t i = 0; i < n_launches; ++i) {
+        a.seq = (int)((first_seq + i) & 0x3fffffff);
+        dp5::dopri5_attempt_kernel<<<grid, dp5::kThreads, smem, s>>>(a);
+    }
+    TCDE_CHECK_CUDA(cudaGetLastError());
+    return TCDE_OK;
+}
+
 extern "C" int tcde_dopri5_linear_attempts(const void* control, int control_kind, int64_t n_rows, const void* knots,
                                            const void* weight, const void* bias, void* state, void* partials, void* ctl,
                                            void* out, const void* out_times, int64_t n_out, int64_t n_paths, int64_t channels,
@@ -477,17 +569,34 @@ extern "C" int tcde_dopri5_linear_attempts(const void* control, int control_kind
     TCDE_CHECK_SUPPORTED(((reinterpret_cast<uintptr_t>(control) | reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                          "device-controlled dopri5: control, state and out must be 16-byte aligned");
     TCDE_CHECK_SUPPORTED(n_paths * 32 * 5 < (1ll << 40), "batch too large");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    constexpr int smem = dp5::Smem::total + 1024;
-    TCDE_CHECK_CUDA(cudaFuncSetAttribute(dp5::dopri5_attempt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = tcde_dopri5_linear_grid(n_paths);
     dp5::Args a{(const float*)control, (const float*)knots, (const float*)weight, (const float*)bias, (float*)state,
                 (double*)partials, (double*)ctl, (float*)out, (const double*)out_times, n_paths, n_rows, control_kind,
-                (int)n_out, 0, (float)sign};
-    for (int64_t i = 0; i < n_launches; ++i) {
-        a.seq = (int)((first_seq + i) & 0x3fffffff);
-        dp5::dopri5_attempt_kernel<<<grid, dp5::kThreads, smem, s>>>(a);
-    }
-    TCDE_CHECK_CUDA(cudaGetLastError());
-    return TCDE_OK;
+                (int)n_out, 0, (float)sign, nullptr, nullptr, n_paths, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return launch_attempts(a, first_seq, n_launches, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tcde_dopri5_linear_paired_attempts(const void* control, int control_kind, int64_t n_rows, const void* knots,
+                                                  const void* weight, const void* bias, const void* weight2, const void* bias2,
+                                                  void* state, void* partials, void* ctl, void* out, const void* out_times,
+                                                  int64_t n_out, int64_t n_ctrl, int64_t channels, int64_t hidden, double sign,
+                                                  void* dump_z, void* dump_a, int32_t* q_index, void* q_frac, void* q_weight,
+                                                  int64_t max_slots, int64_t first_seq, int64_t n_launches, int dtype, void* stream) {
+    TCDE_CHECK_ARG(control && knots && weight && bias && weight2 && bias2 && state && partials && ctl && out && out_times, "null pointer");
+    TCDE_CHECK_ARG(dump_z && dump_a && q_index && q_frac && q_weight && max_slots >= 1 && max_slots < (1ll << 24), "null trajectory / bad slot count");
+    TCDE_CHECK_ARG(n_ctrl >= 1 && n_rows >= 1 && n_out >= 2 && n_launches >= 0 && first_seq >= 0, "bad sizes");
+    TCDE_CHECK_ARG(control_kind == TCDE_CONTROL_CUBIC || control_kind == TCDE_CONTROL_LINEAR, "control_kind=%d", control_kind);
+    TCDE_CHECK_SUPPORTED(dtype == TCDE_F32 && hidden == dp5::kHid && channels == dp5::kCh,
+                         "device-controlled dopri5: built for float32, hidden=32, channels=8");
+    TCDE_CHECK_SUPPORTED(n_ctrl % (dp5::kRows * dp5::kTiles) == 0,
+                         "device-controlled dopri5 adjoint: the batch (%lld paths) must be a multiple of %d", (long long)n_ctrl,
+                         dp5::kRows * dp5::kTiles);
+    TCDE_CHECK_SUPPORTED(((reinterpret_cast<uintptr_t>(control) | reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out) |
+                           reinterpret_cast<uintptr_t>(dump_z) | reinterpret_cast<uintptr_t>(dump_a)) & 15) == 0,
+                         "device-controlled dopri5: control, state, out and the trajectories must be 16-byte aligned");
+    TCDE_CHECK_SUPPORTED(n_ctrl * 2 * 32 * 5 < (1ll << 40), "batch too large");
+    dp5::Args a{(const float*)control, (const float*)knots, (const float*)weight, (const float*)bias, (float*)state,
+                (double*)partials, (double*)ctl, (float*)out, (const double*)out_times, 2 * n_ctrl, n_rows, control_kind,
+                (int)n_out, 0, (float)sign, (const float*)weight2, (const float*)bias2, n_ctrl, (float*)dump_z, (float*)dump_a,
+                q_index, (float*)q_frac, (float*)q_weight, (int)max_slots};
+    return launch_attempts(a, first_seq, n_launches, static_cast<cudaStream_t>(stream));
 }

@@ -10,6 +10,7 @@ any other ``func`` runs through this package's own on-GPU stage loop, which keep
 reference's arithmetic but issues no per-stage host syncs.
 """
 import bisect
+import math
 import warnings
 import weakref
 
@@ -571,9 +572,114 @@ def _kernel_vjp(X, weight, bias, z0, params):
                       _lib.stream_of(yf))
         return ends[1][:, -1].reshape(a_hi.shape)
 
+    def adaptive_segment(t_hi, t_lo, y_hi, a_hi, rtol, atol, gw, gb, slots_hint):
+        """One segment [t_hi -> t_lo] of the dopri5 backward solve with the step controller on the device
+        (``tcde_dopri5_linear_paired_attempts``): the state z and the adjoint state a advance as one virtual batch of
+        2 x paths under one controller, every attempt leaves the inputs of its five weighted stages in the slot of the
+        step it would become, and one launch of the parameter-gradient GEMM over the accepted steps' stages adds
+        dL/dW, dL/db into ``gw`` / ``gb``.  Returns a(t_lo), or None (not built for this problem / out of memory / more
+        accepted steps than slots) -- the caller then runs the host-driven backward."""
+        from . import adaptive
+        lib = _lib.load()
+        yf = y_hi.reshape(-1, hidden).contiguous()
+        af = a_hi.reshape(-1, hidden).contiguous()
+        n_paths = yf.size(0)
+        if hidden != 32 or channels != 8 or n_paths % 256 != 0 or n_paths == 0:
+            return None
+        with torch.cuda.device(z0.device):
+            if not regrouped:
+                regrouped.append(w.view(hidden, channels, hidden).permute(2, 1, 0).contiguous()
+                                 .view(hidden * channels, hidden).neg_())
+                regrouped.append(torch.zeros_like(b))
+            w2, b2 = regrouped
+            if not fields:
+                fields.append(_kernel_field(X, w, b, z0))
+                fields.append(_kernel_field(X, w2, b2, z0))
+
+            def field_v(s_time, v):                  # the virtual batch's slope in s = -t (start slope, Hairer's first step)
+                return torch.cat([-fields[0](-s_time, v[:n_paths]), -fields[1](-s_time, v[n_paths:])])
+
+            s0, s1 = -float(t_hi), -float(t_lo)
+            v0 = torch.cat([yf, af])
+            f0 = field_v(s0, v0)
+            dt = adaptive._initial_step(field_v, s0, v0, f0, rtol, atol)
+            # trajectory slots: enough for a few hundred accepted steps, at most a quarter of the free memory; when they are
+            # full the device pauses, the filled slots are contracted into the gradients and the solve goes on
+            free, _total = torch.cuda.mem_get_info()
+            per_slot = 2 * 5 * n_paths * hidden * 4
+            max_slots = int(min(max(16, slots_hint), 256, 0.25 * free // per_slot))
+            if max_slots < 8:
+                return None
+            dev = z0.device
+            state = torch.empty(5, 2 * n_paths, hidden, dtype=torch.float32, device=dev)
+            state[0].copy_(v0)
+            state[2].copy_(f0)
+            grid = lib.tcde_dopri5_linear_grid(2 * n_paths)
+            partials = torch.zeros(2, grid, dtype=torch.float64, device=dev)
+            ctl_host = torch.zeros(2, 24, dtype=torch.float64)
+            ctl_host[1, 0], ctl_host[1, 1], ctl_host[1, 2] = s0, dt, s1
+            ctl_host[1, 3], ctl_host[1, 4] = rtol, atol
+            ctl_host[1, 10] = 1
+            ctl = ctl_host.to(dev)
+            out = torch.empty(2 * n_paths, 2, hidden, dtype=torch.float32, device=dev)
+            out[:, 0].copy_(v0)
+            out_times = torch.tensor([s0, s1], dtype=torch.float64, device=dev)
+            dump_z = torch.empty(max_slots * 5, n_paths, hidden, dtype=torch.float32, device=dev)
+            dump_a = torch.empty_like(dump_z)
+            q_index = torch.zeros(max_slots * 5, dtype=torch.int32, device=dev)
+            q_frac = torch.zeros(max_slots * 5, dtype=torch.float32, device=dev)
+            q_weight = torch.zeros(max_slots * 5, dtype=torch.float32, device=dev)
+            knots_dev = knots.detach().to(device=dev, dtype=torch.float32).contiguous()
+            stream = _lib.stream_of(yf)
+            scratch_cache = {}
+
+            def contract(n_steps):                   # dL/dW, dL/db += the quadrature over the first n_steps slots
+                n_total = 5 * n_steps
+                if n_total <= 0 or (gw is None and gb is None):
+                    return
+                scratch_bytes = lib.tcde_linear_field_param_grads_scratch_bytes(n_paths, n_total, channels, hidden)
+                if scratch_bytes < 0:
+                    raise RuntimeError("dopri5 adjoint: the parameter-gradient kernel is not built for this problem")
+                if scratch_cache.get("n", 0) < scratch_bytes:
+                    scratch_cache["buf"] = torch.empty(max(scratch_bytes // 4, 4), dtype=torch.float32, device=dev)
+                    scratch_cache["n"] = scratch_bytes
+                _lib.call("tcde_linear_field_param_grads", _lib.ptr(control), kind, n_rows, _lib.ptr(dump_z), _lib.ptr(dump_a),
+                          _lib.ptr(q_index), _lib.ptr(q_frac), _lib.ptr(q_weight), n_total, _lib.ptr(gw), _lib.ptr(gb),
+                          _lib.ptr(scratch_cache["buf"]), n_paths, channels, hidden, 1.0, code, stream)
+
+            seq, base, flushes = 0, 0, 0
+            while True:
+                _lib.call("tcde_dopri5_linear_paired_attempts", _lib.ptr(control), kind, n_rows, _lib.ptr(knots_dev), _lib.ptr(w),
+                          _lib.ptr(b), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(state), _lib.ptr(partials), _lib.ptr(ctl),
+                          _lib.ptr(out), _lib.ptr(out_times), 2, n_paths, channels, hidden, -1.0, _lib.ptr(dump_z),
+                          _lib.ptr(dump_a), _lib.ptr(q_index), _lib.ptr(q_frac), _lib.ptr(q_weight), max_slots, seq,
+                          adaptive._DEVICE_CHUNK, _lib.F32, stream)
+                seq += adaptive._DEVICE_CHUNK
+                last = ctl[(seq - 1) & 1].cpu()
+                if last[6] != 0:
+                    contract(int(last[8]) - base)
+                    if last[15] == 0:
+                        break
+                    # slots full: the filled ones are contracted; hand the slots back and resume where the device paused
+                    base = int(last[8])
+                    flushes += 1
+                    resume = last.clone()
+                    resume[6], resume[15], resume[16] = 0.0, 0.0, float(base)
+                    ctl[(seq - 1) & 1].copy_(resume)
+                    continue
+                if not math.isfinite(float(last[1])) or float(last[1]) == 0.0 or seq > 10_000_000:
+                    raise RuntimeError("dopri5 adjoint: step size underflow / non-finite error estimate at s = {}".format(float(last[0])))
+            n_acc = int(last[8])
+            stage.adaptive_stats = {"n_accepted": n_acc, "n_rejected": int(last[9]), "launches": seq, "slots": max_slots,
+                                    "flushes": flushes}
+            return out[n_paths:, 1].reshape(a_hi.shape).clone()
+
+    fields = []
     stage.launch = launch
     stage.locate_many = locate_many
     stage.segment = segment
+    stage.adaptive_segment = adaptive_segment
+    stage.adaptive_spec = None
     stage.roles = roles
     stage.new_grads = lambda: [torch.zeros_like(w) if r == "w" else torch.zeros_like(b) for r in roles]
     return stage
@@ -804,7 +910,12 @@ def cdeint(X, func, z0, t, adjoint=True, backend="torchdiffeq", **kwargs):
             # (the control's coefficients or knots in ``adjoint_params``): autograd serves the backward solve
             if field_params is None or flipped or t_grad is not None:
                 return None
-            return _kernel_vjp(X, field_params[0], field_params[1], z0, params)
+            st = _kernel_vjp(X, field_params[0], field_params[1], z0, params)
+            if (st is not None and a_method not in FIXED_METHODS and adaptive.device_dopri5_available(z0, sig[2])
+                    and not kwargs.get("adjoint_options", None)):
+                # dopri5 backward with the controller on the device; the forward pass's step count sizes the trajectory slots
+                st.adaptive_spec = (a_rtol, a_atol)
+            return st
 
         fixed_spec = (a_method, a_options.get("step_size", None)) if a_method in FIXED_METHODS else None
         ys = adaptive.solve_with_adjoint(forward_values, autograd_field(), times, solve_aug, z0, adjoint_params,
