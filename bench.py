@@ -159,6 +159,9 @@ class ClockSampler:
                 "samples": len(picked), "window": where}
 
 
+_LOCAL_MS = {}
+
+
 def time_loop(fn, steps, warmup, device, dist=None):
     """W untimed + exactly K timed calls, CUDA events on the current stream, barrier + sync both sides."""
     for _ in range(warmup):
@@ -176,6 +179,7 @@ def time_loop(fn, steps, warmup, device, dist=None):
     if dist is not None:
         dist.barrier()
     ms = start.elapsed_time(end)
+    _LOCAL_MS["last"] = ms                        # this rank's own device time (before the MAX over ranks)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,9 +321,8 @@ def run_gpu_arm(args):
     if args.variant is not None:
         _lib.call("tcde_set_solve_variant", args.variant)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank)       # every rank watches its own GPU; rank 0 reports its own and a per-rank summary
+    sampler.start()
     note("rank {} of {}: generating synthetic data".format(rank, world))
     x, z0, func = synthetic(BATCH, device, seed=1000 + rank)
     if dist is not None:
@@ -339,14 +342,22 @@ def run_gpu_arm(args):
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize(device)
-        if rank == 0:
-            sampler.wait_ready()
+        sampler.wait_ready()
         wall_begin = time.time()
         ms = time_loop(step, args.steps, 0, device, dist)
         wall_end = time.time()
-        if rank == 0:
-            sampler.mark(wall_begin, wall_end)
-        clocks = sampler.stop() if rank == 0 else None
+        sampler.mark(wall_begin, wall_end)
+        clocks = sampler.stop()
+        if dist is not None:
+            # per-rank device time and clocks of the same timed region: `value` uses the slowest rank (time_loop's MAX)
+            mine = {"rank": rank, "ms_per_step": _LOCAL_MS.get("last", 0.0) / args.steps, "sm_mhz": clocks.get("sm_mhz"),
+                    "reasons": clocks.get("reasons")}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            if rank == 0:
+                clocks["per_rank"] = gathered
+        if rank != 0:
+            clocks = None
         assert bool(torch.isfinite(holder["out"]).all())
 
         note("device-resident: {:.3f} ms per solve".format(ms / args.steps))
