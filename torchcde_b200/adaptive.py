@@ -463,7 +463,10 @@ def _device_adaptive_backward(stage, times, ys, grad_ys):
     totals = {}
     a_y = grad_ys[-1].clone()
     for i in range(len(times) - 1, 0, -1):
-        a_lo = stage.adaptive_segment(times[i], times[i - 1], ys[i], a_y, rtol, atol, gw, gb, hint)
+        try:
+            a_lo = stage.adaptive_segment(times[i], times[i - 1], ys[i], a_y, rtol, atol, gw, gb, hint)
+        except NotImplementedError:           # TCDE_ERR_UNSUPPORTED from a kernel: the host-driven backward takes any problem
+            a_lo = None
         if a_lo is None:
             return None
         for key, val in stage.adaptive_stats.items():
