@@ -46,3 +46,53 @@ def test_detach_trick_cpu(kernels_as_formulas):
 
 def test_evaluate_and_derivative_cpu(kernels_as_formulas):
     T.test_evaluate_and_derivative_are_differentiable()
+
+
+def test_device_adaptive_backward_chains_segments_and_falls_back():
+    """Host logic of the dopri5 backward with the controller on the device (adaptive._device_adaptive_backward): segments run
+    from the last output time to the first, every output time injects its incoming gradient, statistics add up, and any
+    segment that cannot run there (None, or an unsupported-shape report from a kernel) hands the whole backward to the
+    host-driven path."""
+    import torch
+    import torchcde_b200 as cde
+    from torchcde_b200 import adaptive
+
+    calls = []
+
+    def make_stage(mode):
+        def stage():
+            pass
+
+        stage.adaptive_spec = (1e-4, 1e-6)
+        stage.roles = ["w", "b"]
+        stage.new_grads = lambda: [torch.zeros(3), torch.zeros(2)]
+        stage.slots_hint = 32
+
+        def adaptive_segment(t_hi, t_lo, y_hi, a_hi, rtol, atol, gw, gb, hint):
+            calls.append((t_hi, t_lo, hint, rtol, atol))
+            if mode == "none" and len(calls) == 2:
+                return None
+            if mode == "unsupported":
+                raise NotImplementedError("shape")
+            gw += 1.0
+            gb += 2.0
+            stage.adaptive_stats = {"n_accepted": 5, "n_rejected": 2, "launches": 48, "slots": hint, "flushes": 1}
+            return a_hi * 2.0                      # a(t_lo) = 2 a(t_hi)
+
+        stage.adaptive_segment = adaptive_segment
+        return stage
+
+    times = [0.0, 1.0, 3.0]
+    ys = torch.zeros(3, 4, 2)
+    grad_ys = torch.stack([torch.full((4, 2), 1.0), torch.full((4, 2), 10.0), torch.full((4, 2), 100.0)])
+    cde.cdeint.last_adjoint_stats = None
+    a_y, grads = adaptive._device_adaptive_backward(make_stage("ok"), times, ys, grad_ys)
+    assert [c[:2] for c in calls] == [(3.0, 1.0), (1.0, 0.0)] and calls[0][2:] == (32, 1e-4, 1e-6)
+    assert torch.equal(a_y, torch.full((4, 2), (100.0 * 2 + 10.0) * 2 + 1.0))
+    assert torch.equal(grads[0], torch.full((3,), 2.0)) and torch.equal(grads[1], torch.full((2,), 4.0))
+    assert cde.cdeint.last_adjoint_stats == {"n_accepted": 10, "n_rejected": 4, "launches": 96, "slots": 32, "flushes": 2,
+                                             "device_controlled": True}
+    calls.clear()
+    assert adaptive._device_adaptive_backward(make_stage("none"), times, ys, grad_ys) is None
+    calls.clear()
+    assert adaptive._device_adaptive_backward(make_stage("unsupported"), times, ys, grad_ys) is None
