@@ -37,28 +37,27 @@ def logsignature_channels(channels, depth):
 
 
 def _window_knots(t, window_length):
-    """log_ode.py:18-40 on the host (``t`` is one dimensional and short): the window end points, where each of them sits
-    in the merged knot sequence, and the end points that are not already knots."""
-    timespan = t[-1] - t[0]
-    num_pieces = (timespan / window_length).ceil().to(int).item()
-    end_t = t[0] + num_pieces * window_length
-    new_t = torch.linspace(t[0], end_t, num_pieces + 1, dtype=t.dtype, device=t.device)
-    new_t = torch.min(new_t, t.max())
-    t_index = 0
-    new_t_unique = []
-    new_t_indices = []
-    for new_t_elem in new_t:
+    """The window end points (in ``t``'s dtype, the last one clipped to the final time), where each of them sits in the merged
+    knot sequence, and the end points that are not already observation times -- the bookkeeping of log_ode.py:18-40 on the
+    host (``t`` is one dimensional and short), as one merge of two sorted lists."""
+    span = t[-1] - t[0]
+    n_windows = int((span / window_length).ceil().item())
+    ends = torch.linspace(t[0], t[0] + n_windows * window_length, n_windows + 1, dtype=t.dtype, device=t.device)
+    ends = torch.min(ends, t.max())
+    knots = t.tolist()
+    rtol, atol = 1e-5, 1e-8                        # torch.allclose's defaults: when an end point counts as an observation time
+    positions, extra = [], []
+    k = 0
+    for end, end_tensor in zip(ends.tolist(), ends):
         while True:
-            lequal = (new_t_elem <= t[t_index])
-            close = new_t_elem.allclose(t[t_index])
-            if lequal or close:
+            same = abs(end - knots[k]) <= atol + rtol * abs(knots[k])
+            if same or end <= knots[k]:
                 break
-            t_index += 1
-        new_t_indices.append(t_index + len(new_t_unique))
-        if close:
-            continue
-        new_t_unique.append(new_t_elem.unsqueeze(0))
-    return new_t, new_t_indices, new_t_unique
+            k += 1
+        positions.append(k + len(extra))
+        if not same:
+            extra.append(end_tensor.unsqueeze(0))
+    return ends, positions, extra
 
 
 def _logsignature_windows(x, depth, window_length, t, _version):
