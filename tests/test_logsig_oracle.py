@@ -45,3 +45,28 @@ def test_chen_identity_and_counts():
     for c, d in ((1, 3), (2, 5), (3, 4), (5, 2)):
         assert lyndon_words(c, d) == O.lyndon_words(c, d)
         assert logsignature_channels(c, d) == len(O.lyndon_words(c, d))
+
+
+def test_window_knots_bookkeeping():
+    """log_ode.py:18-40 as restated in torchcde_b200.log_ode._window_knots: the merged knot sequence stays sorted, every
+    window end sits at the position it is given, end points that coincide with observation times are not duplicated, and
+    the last window is clipped to the final time."""
+    import math
+    import random
+    import torch
+    from torchcde_b200.log_ode import _window_knots
+
+    random.seed(1)
+    for trial in range(300):
+        n = random.randint(2, 30)
+        dtype = random.choice([torch.float32, torch.float64])
+        t = torch.linspace(0, n - 1, n, dtype=dtype) if trial % 3 == 0 else (torch.rand(n, dtype=torch.float64) + 0.05).cumsum(0).to(dtype)
+        wl = random.choice([0.5, 1.0, 2.0, float(t[-1] - t[0]) / random.randint(1, 5), random.uniform(0.3, 4.0)])
+        ends, positions, extra = _window_knots(t, wl)
+        assert float(ends[0]) == float(t[0]) and float(ends[-1]) == float(t[-1])
+        assert ends.numel() == int(math.ceil(float((t[-1] - t[0]) / wl))) + 1 or ends.numel() == int((((t[-1] - t[0]) / wl).ceil()).item()) + 1
+        merged = torch.cat([t] + extra).sort().values if extra else t
+        assert all(b > a for a, b in zip(positions[:-1], positions[1:]))
+        assert merged.numel() == n + len(extra)
+        for e, p in zip(ends.tolist(), positions):
+            assert abs(float(merged[p]) - e) <= 1e-8 + 1e-5 * abs(e)
