@@ -1,17 +1,32 @@
-"""Port of the reference's test/test_tricks.py (gradient plumbing) to the device: gradients must reach the knots,
-the data behind the coefficients, z0, the vector field's parameters and the output times, for rk4 and dopri5, with and
-without the adjoint method; stacked CDEs must not traverse earlier graph twice; parameter gradients must not depend
-on whether the output times require grad.  Same structure and assertions as the reference file (test_tricks.py:21-131)."""
+"""Gradient plumbing on the device -- what the reference checks in test/test_tricks.py:21-131, restated: gradients must reach
+the knots, the data behind the coefficients, z0, the vector field's parameters and the output times, for rk4 and dopri5, with
+and without the adjoint method; stacked CDEs must not traverse an earlier graph twice; parameter gradients must not depend on
+whether the output times require grad.  Plus what the reference does not check: the two routes agree in value, the builders'
+and the controls' backward passes agree with finite differences.
+
+``TCDE_TRICKS_ON_REFERENCE=1`` runs the plumbing tests of this file against the reference package on the CPU (fixed-step
+methods only: the stand-in for torchdiffeq has no dopri5) -- a self-check of the test logic where no GPU exists."""
+import os
+
 import pytest
 import torch
 
-import torchcde_b200 as torchcde
+if os.environ.get("TCDE_TRICKS_ON_REFERENCE"):
+    from oracle.reference_loader import load_reference
+    torchcde = load_reference()
+    DEV = "cpu"
+    METHODS = ("rk4",)
+else:
+    import torchcde_b200 as torchcde
+    DEV = "cuda"
+    METHODS = ("rk4", "dopri5")
 
 pytestmark = pytest.mark.gpu
-DEV = "cuda"
 
 
 class _Func(torch.nn.Module):
+    """z -> sigmoid(z) broadcast over the input channels, plus one learnt offset per channel (one path, asserted)."""
+
     def __init__(self, input_size, hidden_size):
         super(_Func, self).__init__()
         self.input_size = input_size
@@ -25,37 +40,28 @@ class _Func(torch.nn.Module):
         return out
 
 
-def test_grad_paths():
-    for method in ('rk4', 'dopri5'):
-        for adjoint in (True, False):
-            t = torch.linspace(0, 9, 10, device=DEV, requires_grad=True)
-            path = torch.rand(1, 10, 3, device=DEV, requires_grad=True)
-            coeffs = torchcde.natural_cubic_coeffs(path, t)
-            cubic_spline = torchcde.CubicSpline(coeffs, t)
-            z0 = torch.rand(1, 3, device=DEV, requires_grad=True)
-            func = _Func(input_size=3, hidden_size=3)
-            t_ = torch.tensor([0., 9.], device=DEV, requires_grad=True)
+@pytest.mark.parametrize("use_adjoint", [True, False])
+@pytest.mark.parametrize("method", METHODS)
+def test_every_input_receives_a_gradient(method, use_adjoint):
+    knots = torch.linspace(0, 9, 10, device=DEV, requires_grad=True)
+    series = torch.rand(1, 10, 3, device=DEV, requires_grad=True)
+    coeffs = torchcde.natural_cubic_coeffs(series, knots)
+    control = torchcde.CubicSpline(coeffs, knots)
+    start = torch.rand(1, 3, device=DEV, requires_grad=True)
+    field = _Func(input_size=3, hidden_size=3)
+    out_times = torch.tensor([0., 9.], device=DEV, requires_grad=True)
+    leaves = {"knots": knots, "series": series, "z0": start, "field parameter": field.variable, "output times": out_times}
 
-            if adjoint:
-                kwargs = dict(adjoint_params=tuple(func.parameters()) + (coeffs, t))
-            else:
-                kwargs = {}
-            z = torchcde.cdeint(X=cubic_spline, func=func, z0=z0, t=t_, adjoint=adjoint, method=method, rtol=1e-4,
-                                atol=1e-6, **kwargs)
-            assert z.shape == (1, 2, 3)
-            assert t.grad is None
-            assert path.grad is None
-            assert z0.grad is None
-            assert func.variable.grad is None
-            assert t_.grad is None
-            z[:, 1].sum().backward()
-            assert isinstance(t.grad, torch.Tensor), (method, adjoint)
-            assert isinstance(path.grad, torch.Tensor), (method, adjoint)
-            assert isinstance(z0.grad, torch.Tensor), (method, adjoint)
-            assert isinstance(func.variable.grad, torch.Tensor), (method, adjoint)
-            assert isinstance(t_.grad, torch.Tensor), (method, adjoint)
-            for g in (t.grad, path.grad, z0.grad, func.variable.grad, t_.grad):
-                assert bool(torch.isfinite(g).all())
+    extra = {"adjoint_params": tuple(field.parameters()) + (coeffs, knots)} if use_adjoint else {}
+    z = torchcde.cdeint(X=control, func=field, z0=start, t=out_times, adjoint=use_adjoint, method=method, rtol=1e-4,
+                        atol=1e-6, **extra)
+    assert z.shape == (1, 2, 3)
+    for name, leaf in leaves.items():
+        assert leaf.grad is None, name
+    z[:, 1].sum().backward()
+    for name, leaf in leaves.items():
+        assert isinstance(leaf.grad, torch.Tensor), (name, method, use_adjoint)
+        assert bool(torch.isfinite(leaf.grad).all()), (name, method, use_adjoint)
 
 
 def test_gradients_of_the_two_routes_agree():
@@ -88,80 +94,73 @@ def test_gradients_of_the_two_routes_agree():
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-4), (name, float((a - b).abs().max()))
 
 
-def test_stacked_paths():
-    class Record(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, name, x):
-            ctx.name = name
-            return x
+class _OnlyOnce(torch.autograd.Function):
+    """Identity whose backward fails the test when it is entered a second time."""
 
-        @staticmethod
-        def backward(ctx, x):
-            if hasattr(ctx, 'been_here_before'):
-                pytest.fail(ctx.name)
-            ctx.been_here_before = True
-            return None, x
+    @staticmethod
+    def forward(ctx, label, x):
+        ctx.label = label
+        return x
 
-    coeff_paths = [(torchcde.linear_interpolation_coeffs, torchcde.LinearInterpolation),
-                   (torchcde.natural_cubic_coeffs, torchcde.CubicSpline)]
-    for adjoint in (False, True):
-        for first_coeffs, First in coeff_paths:
-            for second_coeffs, Second in coeff_paths:
-                first_path = torch.rand(1, 100, 2, device=DEV, requires_grad=True)
-                first_coeff = first_coeffs(first_path)
-                first_X = First(first_coeff)
-                first_func = _Func(input_size=2, hidden_size=2)
-
-                second_t = torch.linspace(0, 99, 20, device=DEV)
-                if adjoint:
-                    kwargs = dict(adjoint_params=tuple(first_func.parameters()) + (first_coeff,))
-                else:
-                    kwargs = {}
-                second_path = torchcde.cdeint(X=first_X, func=first_func, z0=torch.rand(1, 2, device=DEV),
-                                              t=second_t, adjoint=adjoint, method='rk4', options=dict(step_size=10),
-                                              **kwargs)
-                second_path = Record.apply('second', second_path)
-                second_coeff = second_coeffs(second_path, second_t)
-                second_X = Second(second_coeff, second_t)
-                second_func = _Func(input_size=2, hidden_size=2)
-
-                third_t = torch.linspace(0, 99, 10, device=DEV)
-                if adjoint:
-                    kwargs = dict(adjoint_params=tuple(second_func.parameters()) + (second_coeff, second_t))
-                else:
-                    kwargs = {}
-                third_path = torchcde.cdeint(X=second_X, func=second_func, z0=torch.rand(1, 2, device=DEV),
-                                             t=third_t, adjoint=adjoint, method='rk4', options=dict(step_size=10),
-                                             **kwargs)
-                third_path = Record.apply('third', third_path)
-                assert first_func.variable.grad is None
-                assert second_func.variable.grad is None
-                assert first_path.grad is None
-                third_path[:, -1].sum().backward()
-                assert isinstance(second_func.variable.grad, torch.Tensor)
-                assert isinstance(first_func.variable.grad, torch.Tensor)
-                assert isinstance(first_path.grad, torch.Tensor)
+    @staticmethod
+    def backward(ctx, grad):
+        if getattr(ctx, "visited", False):
+            pytest.fail("the graph behind the {} path was traversed twice".format(ctx.label))
+        ctx.visited = True
+        return None, grad
 
 
-def test_detach_trick():
-    path = torch.rand(1, 10, 3, device=DEV)
-    interp = torchcde.CubicSpline(torchcde.natural_cubic_coeffs(path))
+_KINDS = {"linear": (lambda x, t=None: torchcde.linear_interpolation_coeffs(x, t), lambda c, t=None: torchcde.LinearInterpolation(c, t)),
+          "cubic": (lambda x, t=None: torchcde.natural_cubic_coeffs(x, t), lambda c, t=None: torchcde.CubicSpline(c, t))}
 
-    func = _Func(input_size=3, hidden_size=3)
 
-    for adjoint in (True, False):
-        variable_grads = []
-        z0 = torch.rand(1, 3, device=DEV)
-        for t_grad in (True, False):
-            t_ = torch.tensor([0., 9.], device=DEV, requires_grad=t_grad)
-            z = torchcde.cdeint(X=interp, z0=z0, func=func, t=t_, adjoint=adjoint, method='rk4',
-                                options=dict(step_size=0.5))
-            z[:, -1].sum().backward()
-            variable_grads.append(func.variable.grad.clone())
-            func.variable.grad.zero_()
+@pytest.mark.parametrize("use_adjoint", [False, True])
+@pytest.mark.parametrize("lower", ["linear", "cubic"])
+@pytest.mark.parametrize("upper", ["linear", "cubic"])
+def test_stacked_cdes_backpropagate_once(use_adjoint, lower, upper):
+    """A CDE driven by the solution of another CDE: one backward pass, every graph visited once, gradients down to the data."""
+    def solve(control, field, times, params):
+        extra = {"adjoint_params": params} if use_adjoint else {}
+        return torchcde.cdeint(X=control, func=field, z0=torch.rand(1, 2, device=DEV), t=times, adjoint=use_adjoint,
+                               method="rk4", options={"step_size": 10}, **extra)
 
-        for elem in variable_grads[1:]:
-            assert (elem == variable_grads[0]).all()
+    build_lower, wrap_lower = _KINDS[lower]
+    build_upper, wrap_upper = _KINDS[upper]
+    data = torch.rand(1, 100, 2, device=DEV, requires_grad=True)
+    lower_coeffs = build_lower(data)
+    lower_field = _Func(input_size=2, hidden_size=2)
+    mid_times = torch.linspace(0, 99, 20, device=DEV)
+    mid_path = solve(wrap_lower(lower_coeffs), lower_field, mid_times, tuple(lower_field.parameters()) + (lower_coeffs,))
+    mid_path = _OnlyOnce.apply("middle", mid_path)
+
+    upper_coeffs = build_upper(mid_path, mid_times)
+    upper_field = _Func(input_size=2, hidden_size=2)
+    top_times = torch.linspace(0, 99, 10, device=DEV)
+    top_path = solve(wrap_upper(upper_coeffs, mid_times), upper_field, top_times,
+                     tuple(upper_field.parameters()) + (upper_coeffs, mid_times))
+    top_path = _OnlyOnce.apply("top", top_path)
+
+    for leaf in (lower_field.variable, upper_field.variable, data):
+        assert leaf.grad is None
+    top_path[:, -1].sum().backward()
+    for leaf in (upper_field.variable, lower_field.variable, data):
+        assert isinstance(leaf.grad, torch.Tensor)
+
+
+@pytest.mark.parametrize("use_adjoint", [True, False])
+def test_parameter_gradient_does_not_depend_on_time_requiring_grad(use_adjoint):
+    control = torchcde.CubicSpline(torchcde.natural_cubic_coeffs(torch.rand(1, 10, 3, device=DEV)))
+    field = _Func(input_size=3, hidden_size=3)
+    start = torch.rand(1, 3, device=DEV)
+    seen = []
+    for times_need_grad in (True, False):
+        out_times = torch.tensor([0., 9.], device=DEV, requires_grad=times_need_grad)
+        z = torchcde.cdeint(X=control, z0=start, func=field, t=out_times, adjoint=use_adjoint, method="rk4",
+                            options={"step_size": 0.5})
+        z[:, -1].sum().backward()
+        seen.append(field.variable.grad.clone())
+        field.variable.grad.zero_()
+    assert torch.equal(seen[0], seen[1])
 
 
 @pytest.mark.parametrize("nan", [0.0, 0.3])
