@@ -28,20 +28,26 @@ def kernels_as_formulas(monkeypatch):
     monkeypatch.setattr(T, "DEV", "cpu")
 
 
-def test_grad_paths_cpu(kernels_as_formulas):
-    T.test_grad_paths()
+@pytest.mark.parametrize("use_adjoint", [True, False])
+@pytest.mark.parametrize("method", ["rk4", "dopri5"])
+def test_grad_paths_cpu(kernels_as_formulas, method, use_adjoint):
+    T.test_every_input_receives_a_gradient(method, use_adjoint)
 
 
 def test_two_routes_agree_cpu(kernels_as_formulas):
     T.test_gradients_of_the_two_routes_agree()
 
 
-def test_stacked_paths_cpu(kernels_as_formulas):
-    T.test_stacked_paths()
+@pytest.mark.parametrize("use_adjoint", [False, True])
+@pytest.mark.parametrize("lower", ["linear", "cubic"])
+@pytest.mark.parametrize("upper", ["linear", "cubic"])
+def test_stacked_paths_cpu(kernels_as_formulas, use_adjoint, lower, upper):
+    T.test_stacked_cdes_backpropagate_once(use_adjoint, lower, upper)
 
 
-def test_detach_trick_cpu(kernels_as_formulas):
-    T.test_detach_trick()
+@pytest.mark.parametrize("use_adjoint", [True, False])
+def test_detach_trick_cpu(kernels_as_formulas, use_adjoint):
+    T.test_parameter_gradient_does_not_depend_on_time_requiring_grad(use_adjoint)
 
 
 def test_evaluate_and_derivative_cpu(kernels_as_formulas):
